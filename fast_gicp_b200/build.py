@@ -1,0 +1,61 @@
+"""Build the native library in-tree: fast_gicp_b200/lib/libvgicp_b200.so (sm_100a only, -lineinfo).
+
+    python -m fast_gicp_b200.build [--force]
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libvgicp_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _sources():
+    return [os.path.join(CSRC, "vgicp_b200.cu")]
+
+
+def _deps():
+    out = [os.path.join(ROOT, "include", "vgicp_b200.h")]
+    for f in os.listdir(CSRC):
+        if f.endswith((".cu", ".cuh", ".hpp", ".h")):
+            out.append(os.path.join(CSRC, f))
+    return out
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(d) > t for d in _deps())
+
+
+def build_native(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}  # the image's CC wrapper lacks libgomp specs
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
+                                                                                "-shared", "-o", LIB_PATH] + _sources()
+    subprocess.check_call(cmd, env=env)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,840 @@
+// vgicp_b200.cu -- C-ABI implementation (include/vgicp_b200.h) on top of the kernels in vgicp_kernels.cuh.
+// Replaces fast_gicp::cuda::FastVGICPCudaCore (reference src/fast_gicp/cuda/fast_vgicp_cuda.cu:18-284).
+// Design: one stream per handle, grow-only device buffers (no allocation in steady state), poses passed as kernel
+// arguments (the reference cudaMallocs a device_vector per call, fast_vgicp_cuda.cu:266-267,277-281), one pinned
+// 43-double mailbox for the result of an evaluation.
+#include "../../include/vgicp_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "lsq_math.hpp"
+#include "vgicp_kernels.cuh"
+
+using namespace vgicp;
+
+namespace {
+
+template <typename T>
+struct DevBuf {  // grow-only device array
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 16;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Cloud {
+  DevBuf<float4> pts;
+  DevBuf<int> nbr;
+  DevBuf<float4> covA;
+  DevBuf<float2> covB;
+  int n = 0;
+  int k = 0;           // neighbours per point currently stored (0 = none)
+  bool has_pts = false;
+  bool has_cov = false;
+  void release() { pts.release(); nbr.release(); covA.release(); covB.release(); }
+};
+
+struct VoxelMap {
+  bool created = false;  // GaussianVoxelMap object exists (keeps its first resolution)
+  bool built = false;
+  float res = 1.0f;
+  int init_num_buckets = 8192;  // gaussian_voxelmap.cuh:20
+  int max_scan = 10;            // gaussian_voxelmap.cuh:20
+  int num_buckets = 0;
+  int num_voxels = 0;
+  DevBuf<int4> buckets;
+  DevBuf<VoxelRec> vox;
+  // build scratch
+  DevBuf<int4> coords;
+  DevBuf<int> slots;
+  DevBuf<int> slot_of_point;
+  DevBuf<double> sums;
+  DevBuf<int> counts;
+  void release() { buckets.release(); vox.release(); coords.release(); slots.release(); slot_of_point.release(); sums.release(); counts.release(); }
+};
+
+}  // namespace
+
+struct vgicp_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+
+  double resolution = 1.0;
+  double kernel_width = 0.25;
+  double kernel_max_dist = 3.0;
+  int offset_mode = 1;  // 1 / 7 / 27 = fixed tables, 0 = generic list
+  std::vector<int4> h_offsets;
+  DevBuf<int4> d_offsets;
+
+  Cloud source, target;
+  VoxelMap map;
+
+  bool has_lin = false;
+  Pose lin;  // linearized_x (float)
+
+  DevBuf<unsigned char> staging;
+  DevBuf<double> partials;
+  DevBuf<int> corr_ids;
+  unsigned int* d_ticket = nullptr;
+  int* d_counters = nullptr;  // [0] fail count, [1] num_voxels
+  double* d_out = nullptr;    // 43 doubles
+  double* h_out = nullptr;    // pinned
+  int* h_counters = nullptr;  // pinned
+};
+
+namespace {
+
+int fail(vgicp_handle h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define CU_TRY(h, expr)                                                                                       \
+  do {                                                                                                        \
+    cudaError_t _e = (expr);                                                                                  \
+    if (_e != cudaSuccess) return fail(h, VGICP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define CHECK_HANDLE(h) \
+  if (!(h)) return VGICP_ERR_INVALID_ARGUMENT
+
+struct DeviceGuard {  // every call runs on the handle's device (the reference uses the current device)
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+inline int blocks_for(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+Pose to_pose(const double* T) {  // Eigen::Isometry3d (column-major) -> float image, like trans.cast<float>()
+  Pose p;
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) p.r[r * 3 + c] = (float)T[c * 4 + r];
+    p.t[r] = (float)T[12 + r];
+  }
+  return p;
+}
+
+int set_cloud(vgicp_handle h, Cloud& c, const float* xyz, size_t n, size_t stride) {
+  if (n > 0 && !xyz) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_cloud: null points");
+  if (stride < 12 || (stride % 4) != 0) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_cloud: stride_bytes must be a multiple of 4 and >= 12");
+  if (n > (size_t)0x7fffffff / 64) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_cloud: too many points");
+  CU_TRY(h, c.pts.reserve(n));
+  c.n = (int)n;
+  c.has_pts = true;
+  if (n == 0) return VGICP_OK;
+  CU_TRY(h, h->staging.reserve(n * stride));
+  CU_TRY(h, cudaMemcpyAsync(h->staging.p, xyz, n * stride, cudaMemcpyHostToDevice, h->stream));
+  k_unpack_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->staging.p, stride, (int)n, c.pts.p);
+  h->launches++;
+  CU_TRY(h, cudaGetLastError());
+  // the caller may free/modify xyz after return: pageable copies are staged synchronously by the driver, pinned ones are not
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return VGICP_OK;
+}
+
+int set_neighbors(vgicp_handle h, Cloud& c, int k, const int* idx, size_t nk) {
+  if (!c.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "set_neighbors: cloud not set");
+  if (k <= 0 || !idx || nk != (size_t)k * (size_t)c.n) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_neighbors: k * num_points != neighbors.size()");
+  CU_TRY(h, c.nbr.reserve(nk));
+  CU_TRY(h, cudaMemcpyAsync(c.nbr.p, idx, nk * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  c.k = k;
+  return VGICP_OK;
+}
+
+int find_neighbors(vgicp_handle h, Cloud& c, int k) {
+  if (!c.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "find_neighbors: cloud not set");
+  if (k <= 0 || k > kMaxK || k > c.n) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "find_neighbors: need 1 <= k <= min(num_points, 64)");
+  CU_TRY(h, c.nbr.reserve((size_t)c.n * k));
+  size_t smem = sizeof(float4) * kKnnTile + (size_t)k * kKnnThreads * (sizeof(float) + sizeof(int));
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_TRY(h, cudaFuncSetAttribute(k_knn_bruteforce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float4) * kKnnTile + (size_t)kMaxK * kKnnThreads * 8)));
+    attr_set = true;
+  }
+  k_knn_bruteforce<<<blocks_for(c.n, kKnnThreads), kKnnThreads, smem, h->stream>>>(c.pts.p, c.n, k, c.nbr.p);
+  h->launches++;
+  CU_TRY(h, cudaGetLastError());
+  c.k = k;
+  return VGICP_OK;
+}
+
+int calc_covariances(vgicp_handle h, Cloud& c, int method) {
+  if (!c.has_pts || c.k <= 0) return fail(h, VGICP_ERR_BAD_STATE, "calculate_covariances: cloud and neighbours must be set first");
+  if (method < 0 || method > 4) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "calculate_covariances: bad regularization method");
+  CU_TRY(h, c.covA.reserve(c.n));
+  CU_TRY(h, c.covB.reserve(c.n));
+  if (c.n > 0) {
+    k_covariance_knn<<<blocks_for(c.n, 128), 128, 0, h->stream>>>(c.pts.p, c.nbr.p, c.n, c.k, method, c.covA.p, c.covB.p);
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
+  }
+  c.has_cov = true;
+  if (method == VGICP_REG_NORMALIZED_MIN_EIG)
+    return fail(h, VGICP_ERR_UNSUPPORTED, "unimplemented covariance regularization method was selected (NORMALIZED_MIN_EIG has no GPU path in the reference either); raw covariances kept");
+  return VGICP_OK;
+}
+
+int calc_covariances_rbf(vgicp_handle h, Cloud& c, int method) {
+  if (!c.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "calculate_covariances_rbf: cloud not set");
+  if (method < 0 || method > 4) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "calculate_covariances_rbf: bad regularization method");
+  CU_TRY(h, c.covA.reserve(c.n));
+  CU_TRY(h, c.covB.reserve(c.n));
+  if (c.n > 0) {
+    k_covariance_rbf<<<blocks_for(c.n, 128), 128, 0, h->stream>>>(c.pts.p, c.n, (float)h->kernel_width, (float)h->kernel_max_dist, method, c.covA.p, c.covB.p);
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
+  }
+  c.has_cov = true;
+  if (method == VGICP_REG_NORMALIZED_MIN_EIG) return fail(h, VGICP_ERR_UNSUPPORTED, "unimplemented covariance regularization method was selected; raw covariances kept");
+  return VGICP_OK;
+}
+
+int get_covariances(vgicp_handle h, Cloud& c, float* out9, size_t cap) {
+  if (!c.has_cov) return fail(h, VGICP_ERR_BAD_STATE, "get_covariances: covariances not computed");
+  if (!out9 || cap < (size_t)c.n) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_covariances: buffer too small");
+  std::vector<float4> a(c.n);
+  std::vector<float2> b(c.n);
+  if (c.n) {
+    CU_TRY(h, cudaMemcpyAsync(a.data(), c.covA.p, sizeof(float4) * c.n, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(b.data(), c.covB.p, sizeof(float2) * c.n, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  for (int i = 0; i < c.n; i++) {
+    float* o = out9 + (size_t)i * 9;
+    o[0] = a[i].x; o[1] = a[i].y; o[2] = a[i].z;
+    o[3] = a[i].y; o[4] = a[i].w; o[5] = b[i].x;
+    o[6] = a[i].z; o[7] = b[i].x; o[8] = b[i].y;
+  }
+  return VGICP_OK;
+}
+
+int get_neighbors(vgicp_handle h, Cloud& c, int* out, size_t cap, int* k_out) {
+  if (c.k <= 0) return fail(h, VGICP_ERR_BAD_STATE, "get_neighbors: neighbours not set");
+  if (k_out) *k_out = c.k;
+  size_t need = (size_t)c.n * c.k;
+  if (!out || cap < need) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_neighbors: buffer too small");
+  if (need) {
+    CU_TRY(h, cudaMemcpyAsync(out, c.nbr.p, need * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return VGICP_OK;
+}
+
+// GaussianVoxelMap::create_voxelmap(points, covs): gaussian_voxelmap.cu:233-289
+int build_voxelmap(vgicp_handle h) {
+  Cloud& t = h->target;
+  VoxelMap& m = h->map;
+  if (!t.has_pts || !t.has_cov) return fail(h, VGICP_ERR_BAD_STATE, "create_target_voxelmap: target points and covariances required");
+  if (t.n <= 0) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "create_target_voxelmap: empty target cloud");
+  if (!m.created) {  // fast_vgicp_cuda.cu:259-261: created once with the resolution current at that time
+    m.created = true;
+    m.res = (float)h->resolution;
+  }
+  m.built = false;
+  const int n = t.n;
+  CU_TRY(h, m.coords.reserve(n));
+  CU_TRY(h, m.slot_of_point.reserve(n));
+  k_voxel_coords<<<blocks_for(n, 256), 256, 0, h->stream>>>(t.pts.p, n, m.res, m.coords.p);
+  h->launches++;
+  int B = m.init_num_buckets;
+  for (;; B *= 2) {  // :265 (no upper bound in the reference; bounded here)
+    if (B > (1 << 28)) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "create_target_voxelmap: hash table would exceed 2^28 buckets");
+    CU_TRY(h, m.slots.reserve(B));
+    k_fill_i32<<<blocks_for(B, 256), 256, 0, h->stream>>>(m.slots.p, -1, (size_t)B);
+    CU_TRY(h, cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(int), h->stream));
+    k_table_insert<<<blocks_for(n, 256), 256, 0, h->stream>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan);
+    k_table_lookup_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan, m.slot_of_point.p, h->d_counters);
+    h->launches += 3;
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if ((double)h->h_counters[0] / (double)n < 0.01) break;  // :280
+  }
+  m.num_buckets = B;
+  CU_TRY(h, m.buckets.reserve(B));
+  k_table_assign_ids<<<1, 1024, 0, h->stream>>>(m.coords.p, m.slots.p, B, m.buckets.p, h->d_counters + 1);
+  h->launches++;
+  CU_TRY(h, cudaMemcpyAsync(h->h_counters + 1, h->d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  const int V = h->h_counters[1];
+  m.num_voxels = V;
+  CU_TRY(h, m.vox.reserve(V > 0 ? V : 1));
+  CU_TRY(h, m.sums.reserve((size_t)(V > 0 ? V : 1) * 10));
+  CU_TRY(h, m.counts.reserve(V > 0 ? V : 1));
+  if (V > 0) {
+    CU_TRY(h, cudaMemsetAsync(m.sums.p, 0, sizeof(double) * 10 * (size_t)V, h->stream));
+    CU_TRY(h, cudaMemsetAsync(m.counts.p, 0, sizeof(int) * (size_t)V, h->stream));
+    k_voxel_accumulate<<<blocks_for(n, 256), 256, 0, h->stream>>>(t.pts.p, t.covA.p, t.covB.p, n, m.slot_of_point.p, m.buckets.p, m.sums.p, m.counts.p);
+    k_voxel_finalize<<<blocks_for(V, 256), 256, 0, h->stream>>>(m.sums.p, m.counts.p, V, m.vox.p);
+    h->launches += 2;
+    CU_TRY(h, cudaGetLastError());
+  }
+  m.built = true;
+  return VGICP_OK;
+}
+
+// one evaluation: launches the fused lookup+derivative kernel; result lands in h->h_out after the stream sync
+int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H) {
+  Cloud& s = h->source;
+  VoxelMap& m = h->map;
+  LinArgs a;
+  a.pts = s.pts.p; a.covA = s.covA.p; a.covB = s.covB.p; a.n = s.n;
+  a.buckets = m.buckets.p; a.mask = (unsigned)(m.num_buckets - 1); a.max_scan = m.max_scan; a.vox = m.vox.p;
+  a.offsets = h->d_offsets.p; a.n_off = (int)h->h_offsets.size(); a.res = m.res;
+  a.Tlin = h->lin; a.Teval = Teval;
+  a.partials = h->partials.p; a.ticket = h->d_ticket; a.out = h->d_out;
+  int grid = blocks_for(s.n > 0 ? s.n : 1, kLinThreads);
+  if (grid > kLinMaxBlocks) grid = kLinMaxBlocks;
+#define LAUNCH_LIN(MODE)                                                            \
+  do {                                                                              \
+    if (want_H) k_linearize<MODE, true><<<grid, kLinThreads, 0, h->stream>>>(a);    \
+    else k_linearize<MODE, false><<<grid, kLinThreads, 0, h->stream>>>(a);          \
+  } while (0)
+  switch (h->offset_mode) {
+    case 1: LAUNCH_LIN(1); break;
+    case 7: LAUNCH_LIN(7); break;
+    case 27: LAUNCH_LIN(27); break;
+    default: LAUNCH_LIN(0); break;
+  }
+#undef LAUNCH_LIN
+  h->launches++;
+  CU_TRY(h, cudaGetLastError());
+  return VGICP_OK;
+}
+
+int check_ready_for_eval(vgicp_handle h, const char* who) {
+  if (!h->source.has_pts || !h->source.has_cov) return fail(h, VGICP_ERR_BAD_STATE, std::string(who) + ": source points and covariances required");
+  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, std::string(who) + ": target voxel map not built");
+  if (!h->has_lin) return fail(h, VGICP_ERR_BAD_STATE, std::string(who) + ": update_correspondences has not been called");
+  return VGICP_OK;
+}
+
+int evaluate(vgicp_handle h, const double* T, double* H36, double* b6, double* err) {
+  const bool want_H = (H36 != nullptr && b6 != nullptr);  // compute_derivatives.cu:160
+  int rc = launch_linearize(h, to_pose(T), want_H);
+  if (rc) return rc;
+  CU_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * (want_H ? 43 : 1), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (err) *err = h->h_out[0];
+  if (want_H) {
+    memcpy(H36, h->h_out + 1, 36 * sizeof(double));
+    memcpy(b6, h->h_out + 37, 6 * sizeof(double));
+  }
+  return VGICP_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+const char* vgicp_version(void) { return "vgicp_b200 0.1 (sm_100a)"; }
+
+int vgicp_create(int device, vgicp_handle* out) {
+  if (!out) return VGICP_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return VGICP_ERR_NO_DEVICE;
+  if (device < 0 || device >= ndev) return VGICP_ERR_INVALID_ARGUMENT;
+  vgicp_context* h = new (std::nothrow) vgicp_context();
+  if (!h) return VGICP_ERR_CUDA;
+  h->device = device;
+  DeviceGuard g(device);
+  // the kernel image is sm_100a only: fail loudly on anything else instead of falling back
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, k_linearize<1, true>) != cudaSuccess) {
+    cudaGetLastError();
+    delete h;
+    return VGICP_ERR_NO_DEVICE;
+  }
+  bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->d_ticket, sizeof(unsigned int)) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->d_counters, 4 * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->d_out, 64 * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&h->h_out, 64 * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&h->h_counters, 4 * sizeof(int)) == cudaSuccess;
+  ok = ok && h->partials.reserve((size_t)kLinMaxBlocks * kLinValues) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream) == cudaSuccess;
+  ok = ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
+  if (!ok) {
+    vgicp_destroy(h);
+    return VGICP_ERR_CUDA;
+  }
+  h->h_offsets.assign(1, make_int4(0, 0, 0, 0));  // fast_vgicp_cuda.cu:28-29
+  h->offset_mode = 1;
+  *out = h;
+  return VGICP_OK;
+}
+
+int vgicp_destroy(vgicp_handle h) {
+  if (!h) return VGICP_OK;
+  DeviceGuard g(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->source.release();
+  h->target.release();
+  h->map.release();
+  h->d_offsets.release();
+  h->staging.release();
+  h->partials.release();
+  h->corr_ids.release();
+  if (h->d_ticket) cudaFree(h->d_ticket);
+  if (h->d_counters) cudaFree(h->d_counters);
+  if (h->d_out) cudaFree(h->d_out);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->h_counters) cudaFreeHost(h->h_counters);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return VGICP_OK;
+}
+
+const char* vgicp_last_error(vgicp_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int vgicp_set_resolution(vgicp_handle h, double resolution) {
+  CHECK_HANDLE(h);
+  if (!(resolution > 0.0)) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_resolution: resolution must be positive");
+  h->resolution = resolution;
+  return VGICP_OK;
+}
+
+int vgicp_set_kernel_params(vgicp_handle h, double kernel_width, double kernel_max_dist) {
+  CHECK_HANDLE(h);
+  h->kernel_width = kernel_width;
+  h->kernel_max_dist = kernel_max_dist;
+  return VGICP_OK;
+}
+
+int vgicp_set_neighbor_search_method(vgicp_handle h, int method, double radius) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  std::vector<int4> off;
+  int mode = 0;
+  switch (method) {
+    case VGICP_DIRECT1:
+      off.push_back(make_int4(0, 0, 0, 0));
+      mode = 1;
+      break;
+    case VGICP_DIRECT7: {  // order of fast_vgicp_cuda.cu:57-63
+      const int o[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+      for (auto& v : o) off.push_back(make_int4(v[0], v[1], v[2], 0));
+      mode = 7;
+    } break;
+    case VGICP_DIRECT27:  // :68-74, i-major
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+          for (int k = 0; k < 3; k++) off.push_back(make_int4(i - 1, j - 1, k - 1, 0));
+      mode = 27;
+      break;
+    case VGICP_DIRECT_RADIUS: {  // :79-88
+      if (!(radius >= 0.0) || radius > 64.0) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_neighbor_search_method: radius out of range");
+      int range = (int)ceil(radius);
+      for (int i = -range; i <= range; i++)
+        for (int j = -range; j <= range; j++)
+          for (int k = -range; k <= range; k++) {
+            double nrm = sqrt((double)i * i + (double)j * j + (double)k * k);
+            if (nrm <= radius + 1e-3) off.push_back(make_int4(i, j, k, 0));
+          }
+      mode = 0;
+    } break;
+    default:  // the reference abort()s here (fast_vgicp_cuda.cu:46-48)
+      return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_neighbor_search_method: unknown method");
+  }
+  CU_TRY(h, h->d_offsets.reserve(off.size()));
+  if (!off.empty()) {
+    CU_TRY(h, cudaMemcpyAsync(h->d_offsets.p, off.data(), off.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  h->h_offsets.swap(off);
+  h->offset_mode = mode;
+  return VGICP_OK;
+}
+
+int vgicp_set_source_cloud(vgicp_handle h, const float* xyz, size_t n, size_t stride_bytes) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  h->source.k = 0;  // the reference keeps stale neighbours/covariances; every caller recomputes them right after
+  h->source.has_cov = false;
+  return set_cloud(h, h->source, xyz, n, stride_bytes);
+}
+
+int vgicp_set_target_cloud(vgicp_handle h, const float* xyz, size_t n, size_t stride_bytes) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  h->target.k = 0;
+  h->target.has_cov = false;
+  h->map.built = false;
+  return set_cloud(h, h->target, xyz, n, stride_bytes);
+}
+
+int vgicp_swap_source_and_target(vgicp_handle h) {  // fast_vgicp_cuda.cu:97-107
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  std::swap(h->source, h->target);
+  h->map.built = false;
+  if (!h->target.has_pts || !h->target.has_cov) return VGICP_OK;
+  return build_voxelmap(h);
+}
+
+int vgicp_set_source_neighbors(vgicp_handle h, int k, const int* indices, size_t n_times_k) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return set_neighbors(h, h->source, k, indices, n_times_k);
+}
+int vgicp_set_target_neighbors(vgicp_handle h, int k, const int* indices, size_t n_times_k) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return set_neighbors(h, h->target, k, indices, n_times_k);
+}
+int vgicp_find_source_neighbors(vgicp_handle h, int k) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return find_neighbors(h, h->source, k);
+}
+int vgicp_find_target_neighbors(vgicp_handle h, int k) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return find_neighbors(h, h->target, k);
+}
+int vgicp_calculate_source_covariances(vgicp_handle h, int method) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return calc_covariances(h, h->source, method);
+}
+int vgicp_calculate_target_covariances(vgicp_handle h, int method) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return calc_covariances(h, h->target, method);
+}
+int vgicp_calculate_source_covariances_rbf(vgicp_handle h, int method) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return calc_covariances_rbf(h, h->source, method);
+}
+int vgicp_calculate_target_covariances_rbf(vgicp_handle h, int method) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return calc_covariances_rbf(h, h->target, method);
+}
+int vgicp_get_source_covariances(vgicp_handle h, float* out9, size_t cap) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return get_covariances(h, h->source, out9, cap);
+}
+int vgicp_get_target_covariances(vgicp_handle h, float* out9, size_t cap) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return get_covariances(h, h->target, out9, cap);
+}
+int vgicp_get_source_neighbors(vgicp_handle h, int* out, size_t cap, int* k_out) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return get_neighbors(h, h->source, out, cap, k_out);
+}
+int vgicp_get_target_neighbors(vgicp_handle h, int* out, size_t cap, int* k_out) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return get_neighbors(h, h->target, out, cap, k_out);
+}
+int vgicp_get_num_source_points(vgicp_handle h, size_t* n) {
+  CHECK_HANDLE(h);
+  if (!n) return VGICP_ERR_INVALID_ARGUMENT;
+  *n = h->source.has_pts ? (size_t)h->source.n : 0;
+  return VGICP_OK;
+}
+int vgicp_get_num_target_points(vgicp_handle h, size_t* n) {
+  CHECK_HANDLE(h);
+  if (!n) return VGICP_ERR_INVALID_ARGUMENT;
+  *n = h->target.has_pts ? (size_t)h->target.n : 0;
+  return VGICP_OK;
+}
+
+int vgicp_create_target_voxelmap(vgicp_handle h) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return build_voxelmap(h);
+}
+
+int vgicp_get_num_voxels(vgicp_handle h, int* nv) {
+  CHECK_HANDLE(h);
+  if (!nv) return VGICP_ERR_INVALID_ARGUMENT;
+  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "voxel map not built");
+  *nv = h->map.num_voxels;
+  return VGICP_OK;
+}
+int vgicp_get_num_buckets(vgicp_handle h, int* nb) {
+  CHECK_HANDLE(h);
+  if (!nb) return VGICP_ERR_INVALID_ARGUMENT;
+  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "voxel map not built");
+  *nb = h->map.num_buckets;
+  return VGICP_OK;
+}
+
+static int fetch_voxels(vgicp_handle h, std::vector<VoxelRec>& v) {
+  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "voxel map not built");
+  v.resize(h->map.num_voxels);
+  if (!v.empty()) {
+    CU_TRY(h, cudaMemcpyAsync(v.data(), h->map.vox.p, sizeof(VoxelRec) * v.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return VGICP_OK;
+}
+
+int vgicp_get_voxel_num_points(vgicp_handle h, int* out, size_t cap) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  std::vector<VoxelRec> v;
+  int rc = fetch_voxels(h, v);
+  if (rc) return rc;
+  if (!out || cap < v.size()) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_voxel_num_points: buffer too small");
+  for (size_t i = 0; i < v.size(); i++) memcpy(&out[i], &v[i].mean_n.w, sizeof(int));
+  return VGICP_OK;
+}
+int vgicp_get_voxel_means(vgicp_handle h, float* out3, size_t cap) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  std::vector<VoxelRec> v;
+  int rc = fetch_voxels(h, v);
+  if (rc) return rc;
+  if (!out3 || cap < v.size()) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_voxel_means: buffer too small");
+  for (size_t i = 0; i < v.size(); i++) {
+    out3[3 * i] = v[i].mean_n.x; out3[3 * i + 1] = v[i].mean_n.y; out3[3 * i + 2] = v[i].mean_n.z;
+  }
+  return VGICP_OK;
+}
+int vgicp_get_voxel_covs(vgicp_handle h, float* out9, size_t cap) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  std::vector<VoxelRec> v;
+  int rc = fetch_voxels(h, v);
+  if (rc) return rc;
+  if (!out9 || cap < v.size()) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_voxel_covs: buffer too small");
+  for (size_t i = 0; i < v.size(); i++) {
+    float* o = out9 + 9 * i;
+    const float4 a = v[i].c0, b = v[i].c1;
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.y; o[4] = a.w; o[5] = b.x; o[6] = a.z; o[7] = b.x; o[8] = b.y;
+  }
+  return VGICP_OK;
+}
+int vgicp_get_voxel_buckets(vgicp_handle h, int* coords3, int* ids, size_t cap) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "voxel map not built");
+  size_t B = (size_t)h->map.num_buckets;
+  if (cap < B || !coords3 || !ids) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_voxel_buckets: buffer too small");
+  std::vector<int4> b(B);
+  CU_TRY(h, cudaMemcpyAsync(b.data(), h->map.buckets.p, sizeof(int4) * B, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < B; i++) {
+    coords3[3 * i] = b[i].x; coords3[3 * i + 1] = b[i].y; coords3[3 * i + 2] = b[i].z;
+    ids[i] = b[i].w;
+  }
+  return VGICP_OK;
+}
+
+int vgicp_update_correspondences(vgicp_handle h, const double T[16]) {  // fast_vgicp_cuda.cu:265-274
+  CHECK_HANDLE(h);
+  if (!T) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "update_correspondences: null pose");
+  if (!h->source.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "update_correspondences: source cloud not set");
+  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "update_correspondences: target voxel map not built");
+  h->lin = to_pose(T);  // linearized_x = trans.cast<float>()
+  h->has_lin = true;
+  // the lookup itself is fused into the evaluation kernel; the explicit list is only built by the getter
+  return VGICP_OK;
+}
+
+int vgicp_get_voxel_correspondences(vgicp_handle h, int* pairs, size_t cap, size_t* n_pairs) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (!h->source.has_pts || !h->map.built || !h->has_lin) return fail(h, VGICP_ERR_BAD_STATE, "get_voxel_correspondences: update_correspondences has not been called");
+  const int n = h->source.n;
+  const int n_off = (int)h->h_offsets.size();
+  size_t total = (size_t)n * n_off;
+  std::vector<int> ids(total);
+  if (total) {
+    CU_TRY(h, h->corr_ids.reserve(total));
+    k_correspondence_ids<<<blocks_for(n, 128), 128, 0, h->stream>>>(h->source.pts.p, n, h->map.buckets.p, (unsigned)(h->map.num_buckets - 1), h->map.max_scan, h->d_offsets.p, n_off,
+                                                                     h->map.res, h->lin, h->corr_ids.p);
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(ids.data(), h->corr_ids.p, total * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  size_t cnt = 0;
+  for (int o = 0; o < n_off; o++)
+    for (int i = 0; i < n; i++) {
+      int id = ids[(size_t)o * n + i];
+      if (id < 0) continue;  // remove_if(invalid_correspondence_kernel), find_voxel_correspondences.cu:109-110
+      if (pairs && cnt < cap) { pairs[2 * cnt] = i; pairs[2 * cnt + 1] = id; }
+      cnt++;
+    }
+  if (n_pairs) *n_pairs = cnt;
+  if (pairs && cnt > cap) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_voxel_correspondences: buffer too small");
+  return VGICP_OK;
+}
+
+int vgicp_compute_error(vgicp_handle h, const double T[16], double* H36, double* b6, double* err) {  // fast_vgicp_cuda.cu:276-284
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (!T) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "compute_error: null pose");
+  int rc = check_ready_for_eval(h, "compute_error");
+  if (rc) return rc;
+  return evaluate(h, T, H36, b6, err);
+}
+
+void vgicp_lsq_default_params(vgicp_lsq_params* p) {  // lsq_registration_impl.hpp:9-22
+  if (!p) return;
+  p->max_iterations = 64;
+  p->rotation_epsilon = 2e-3;
+  p->transformation_epsilon = 5e-4;
+  p->use_gauss_newton = 0;
+  p->lm_max_iterations = 10;
+  p->lm_init_lambda_factor = 1e-9;
+}
+
+// LsqRegistration::computeTransformation (lsq_registration_impl.hpp:53-79) with step_gn (:106-120) / step_lm (:123-168);
+// linearize = update_correspondences + compute_error (fast_vgicp_cuda_impl.hpp:170-173).
+int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* params, vgicp_align_result* res) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (!guess || !res) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "align: null argument");
+  vgicp_lsq_params P;
+  if (params) P = *params; else vgicp_lsq_default_params(&P);
+  if (!h->source.has_pts || !h->source.has_cov) return fail(h, VGICP_ERR_BAD_STATE, "align: source points and covariances required");
+  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "align: target voxel map not built");
+
+  Iso3d x0;
+  memcpy(x0.m, guess, sizeof(x0.m));
+  double lambda = -1.0;
+  bool converged = false;
+  memset(res, 0, sizeof(*res));
+  for (int i = 0; i < 6; i++) res->H[i * 7] = 1.0;  // final_hessian_.setIdentity()
+  for (int it = 0; it < P.max_iterations && !converged; it++) {
+    res->nr_iterations = it;
+    double H[36], b[6], nb[6], d[6], y0 = 0.0;
+    h->lin = to_pose(x0.m);
+    h->has_lin = true;
+    int rc = evaluate(h, x0.m, H, b, &y0);
+    if (rc) return rc;
+    res->n_linearize++;
+    for (int j = 0; j < 6; j++) nb[j] = -b[j];
+    Iso3d delta = iso_identity();
+    bool ok = false;
+    if (P.use_gauss_newton) {
+      ldlt_solve6(H, nb, d);
+      delta = se3_exp(d);
+      x0 = iso_mul(delta, x0);
+      memcpy(res->H, H, sizeof(H));
+      ok = true;
+    } else {
+      if (lambda < 0.0) {
+        double mx = 0.0;
+        for (int j = 0; j < 6; j++) mx = fmax(mx, fabs(H[j * 7]));
+        lambda = P.lm_init_lambda_factor * mx;
+      }
+      double nu = 2.0;
+      for (int j = 0; j < P.lm_max_iterations; j++) {
+        double Hl[36];
+        memcpy(Hl, H, sizeof(H));
+        for (int q = 0; q < 6; q++) Hl[q * 7] += lambda;
+        ldlt_solve6(Hl, nb, d);
+        delta = se3_exp(d);
+        Iso3d xi = iso_mul(delta, x0);
+        double yi = 0.0;
+        rc = evaluate(h, xi.m, nullptr, nullptr, &yi);
+        if (rc) return rc;
+        res->n_compute_error++;
+        double den = 0.0;
+        for (int q = 0; q < 6; q++) den += d[q] * (lambda * d[q] - b[q]);
+        double rho = (y0 - yi) / den;
+        if (rho < 0) {
+          if (is_converged(delta, P.rotation_epsilon, P.transformation_epsilon)) { ok = true; break; }
+          lambda = nu * lambda;
+          nu = 2 * nu;
+          continue;
+        }
+        x0 = xi;
+        double f = 1.0 - pow(2.0 * rho - 1.0, 3);
+        lambda = lambda * fmax(1.0 / 3.0, f);
+        memcpy(res->H, H, sizeof(H));
+        ok = true;
+        break;
+      }
+    }
+    if (!ok) { res->lm_failed = 1; break; }  // "lm not converged!!"
+    converged = is_converged(delta, P.rotation_epsilon, P.transformation_epsilon);
+  }
+  memcpy(res->T, x0.m, sizeof(x0.m));
+  res->converged = converged ? 1 : 0;
+  return VGICP_OK;
+}
+
+int vgicp_transform_source(vgicp_handle h, const double T[16], float* out_xyz, size_t cap, size_t stride) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (!T || !out_xyz) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "transform_source: null argument");
+  if (!h->source.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "transform_source: source cloud not set");
+  const int n = h->source.n;
+  if (cap < (size_t)n || stride < 12 || stride % 4) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "transform_source: bad capacity/stride");
+  if (n == 0) return VGICP_OK;
+  CU_TRY(h, h->staging.reserve((size_t)n * stride));
+  // keep the non-xyz bytes of the caller's records untouched: copy in, overwrite xyz, copy out
+  CU_TRY(h, cudaMemcpyAsync(h->staging.p, out_xyz, (size_t)n * stride, cudaMemcpyHostToDevice, h->stream));
+  k_transform_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->source.pts.p, n, to_pose(T), h->staging.p, stride);
+  h->launches++;
+  CU_TRY(h, cudaGetLastError());
+  CU_TRY(h, cudaMemcpyAsync(out_xyz, h->staging.p, (size_t)n * stride, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return VGICP_OK;
+}
+
+int vgicp_get_launch_count(vgicp_handle h, uint64_t* launches) {
+  CHECK_HANDLE(h);
+  if (!launches) return VGICP_ERR_INVALID_ARGUMENT;
+  *launches = h->launches;
+  return VGICP_OK;
+}
+
+int vgicp_synchronize(vgicp_handle h) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return VGICP_OK;
+}
+
+int vgicp_get_stream(vgicp_handle h, uint64_t* stream) {
+  CHECK_HANDLE(h);
+  if (!stream) return VGICP_ERR_INVALID_ARGUMENT;
+  *stream = (uint64_t)(uintptr_t)h->stream;
+  return VGICP_OK;
+}
+
+}  // extern "C"

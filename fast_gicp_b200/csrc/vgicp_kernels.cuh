@@ -1,0 +1,813 @@
+// vgicp_kernels.cuh -- hand-written sm_100a kernels of the VGICP hot path.
+//
+// Stage 1  k-NN + covariance + regularisation   (reference: brute_force_knn.cu, covariance_estimation.cu,
+//                                                covariance_estimation_rbf.cu, covariance_regularization.cu)
+// Stage 2  Gaussian voxel map build              (reference: gaussian_voxelmap.cu, vector3_hash.cuh)
+// Stage 3  fused voxel lookup + Mahalanobis residual/Jacobian reduction
+//                                                (reference: find_voxel_correspondences.cu + compute_derivatives.cu)
+//
+// Device data layout (all arrays 16-byte aligned, one element per point / voxel / bucket):
+//   points      float4 {x,y,z,0}                          16 B/pt   coalesced LDG.128
+//   covariance  float4 {xx,xy,xz,yy} + float2 {yz,zz}     24 B/pt   symmetric-packed (reference: 36 B Matrix3f)
+//   neighbours  int32  [n][k]
+//   buckets     int4   {cx,cy,cz,voxel id | -1}           16 B/bucket  == thrust::pair<Vector3i,int>
+//   voxels      3 x float4: {mx,my,mz,n(int bits)} {cxx,cxy,cxz,cyy} {cyz,czz,-,-}   48 B/voxel
+//
+// Arithmetic that the parity contract makes order-defined (voxel coordinate, hash, transformed point, k-NN distance,
+// raw covariance) is written with explicit __f*_rn / __fmaf_rn so nvcc cannot re-associate or contract it differently
+// from the CPU checker used by the tests (which spells the same operations).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vgicp {
+
+constexpr int kMaxK = 64;            // k-NN list capacity
+constexpr int kKnnThreads = 128;     // queries per block in the brute-force k-NN
+constexpr int kKnnTile = 512;        // targets staged in shared memory per step
+constexpr int kLinThreads = 128;     // block size of the linearize kernel
+constexpr int kLinMaxBlocks = 592;   // 4 x 148 SMs: upper bound on partial sums the last block has to fold
+constexpr int kLinValues = 28;       // 21 unique H + 6 b + 1 err
+constexpr int kRbfBlock = 512;       // covariance_estimation_rbf.cu:60 BLOCK_SIZE
+
+struct Pose {      // float image of an Eigen::Isometry3f: R row-major here, t
+  float r[9];
+  float t[3];
+};
+
+struct VoxelRec {
+  float4 mean_n;  // mean xyz, num_points as int bits in w
+  float4 c0;      // cxx cxy cxz cyy
+  float4 c1;      // cyz czz 0 0
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// vector3_hash.cuh:8-38
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t hash_mix(uint64_t k) {
+  const uint64_t m = 0xc6a4a7935bd1e995ULL;
+  k *= m;
+  k ^= k >> 47;
+  k *= m;
+  return k;
+}
+__host__ __device__ __forceinline__ uint64_t hash_fold(uint64_t h, uint64_t kmixed) {
+  const uint64_t m = 0xc6a4a7935bd1e995ULL;
+  h ^= kmixed;
+  h *= m;
+  h += 0xe6546b64ULL;
+  return h;
+}
+// vector3i_hash: the int -> uint64_t conversion sign-extends (vector3_hash.cuh:29-31)
+__host__ __device__ __forceinline__ uint64_t vector3i_hash(int x, int y, int z) {
+  uint64_t h = 0;
+  h = hash_fold(h, hash_mix((uint64_t)(int64_t)x));
+  h = hash_fold(h, hash_mix((uint64_t)(int64_t)y));
+  h = hash_fold(h, hash_mix((uint64_t)(int64_t)z));
+  return h;
+}
+
+// calc_voxel_coord (vector3_hash.cuh:35-38): floor(x / res - 0.5) in float
+__device__ __forceinline__ int voxel_coord1(float x, float res) { return (int)floorf(__fsub_rn(__fdiv_rn(x, res), 0.5f)); }
+
+// R*a + t the way nvcc contracts Eigen's expression: fma(r2,a2, fma(r1,a1, r0*a0)) + t
+__device__ __forceinline__ float3 transform_point(const Pose& T, float ax, float ay, float az) {
+  float3 o;
+  o.x = __fadd_rn(__fmaf_rn(T.r[2], az, __fmaf_rn(T.r[1], ay, __fmul_rn(T.r[0], ax))), T.t[0]);
+  o.y = __fadd_rn(__fmaf_rn(T.r[5], az, __fmaf_rn(T.r[4], ay, __fmul_rn(T.r[3], ax))), T.t[1]);
+  o.z = __fadd_rn(__fmaf_rn(T.r[8], az, __fmaf_rn(T.r[7], ay, __fmul_rn(T.r[6], ax))), T.t[2]);
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cloud upload: strided host xyz image -> float4
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_unpack_points(const unsigned char* __restrict__ raw, size_t stride, int n, float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+  out[i] = make_float4(p[0], p[1], p[2], 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stage 1a: exact brute-force k-NN inside one cloud (self included).  One query per thread, targets staged through
+// shared memory in tiles (every thread reads the same target -> broadcast, conflict-free), per-thread ascending
+// top-k list in shared memory laid out [k][thread] (conflict-free).  d2 = (dx*dx + dy*dy) + dz*dz, no contraction.
+// Replaces brute_force_knn.cu:16-60 (global-memory heap per thread) and the CPU kd-tree of
+// fast_vgicp_cuda_impl.hpp:152-167.  Output rows ascending in (d2, index).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kKnnThreads) k_knn_bruteforce(const float4* __restrict__ pts, int n, int k, int* __restrict__ nbr) {
+  extern __shared__ float smem_knn[];
+  float4* tile = reinterpret_cast<float4*>(smem_knn);                       // kKnnTile float4
+  float* ld = smem_knn + 4 * kKnnTile;                                      // [k][kKnnThreads]
+  int* li = reinterpret_cast<int*>(ld + (size_t)k * kKnnThreads);           // [k][kKnnThreads]
+  const int tid = threadIdx.x;
+  const int q = blockIdx.x * kKnnThreads + tid;
+  const bool active = q < n;
+  float4 qp = active ? pts[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < k; j++) {
+    ld[j * kKnnThreads + tid] = __int_as_float(0x7f800000);  // +inf
+    li[j * kKnnThreads + tid] = -1;
+  }
+  float worst = __int_as_float(0x7f800000);
+  for (int base = 0; base < n; base += kKnnTile) {
+    __syncthreads();
+    for (int j = tid; j < kKnnTile; j += kKnnThreads) {
+      int g = base + j;
+      tile[j] = g < n ? pts[g] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    if (!active) continue;
+    const int lim = min(kKnnTile, n - base);
+#pragma unroll 4
+    for (int j = 0; j < lim; j++) {
+      float4 t = tile[j];
+      float dx = __fsub_rn(t.x, qp.x), dy = __fsub_rn(t.y, qp.y), dz = __fsub_rn(t.z, qp.z);
+      float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (d < worst) {  // targets arrive in increasing index, so ties keep the smaller index: ascending (d2, index)
+        int p = k - 1;
+        while (p > 0 && ld[(p - 1) * kKnnThreads + tid] > d) {
+          ld[p * kKnnThreads + tid] = ld[(p - 1) * kKnnThreads + tid];
+          li[p * kKnnThreads + tid] = li[(p - 1) * kKnnThreads + tid];
+          p--;
+        }
+        ld[p * kKnnThreads + tid] = d;
+        li[p * kKnnThreads + tid] = base + j;
+        worst = ld[(k - 1) * kKnnThreads + tid];
+      }
+    }
+  }
+  if (active)
+    for (int j = 0; j < k; j++) nbr[(size_t)q * k + j] = li[j * kKnnThreads + tid];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 helpers (registers).  Full matrices are row-major m[r*3+c] here.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void inv3_general(const float* m, float* o) {  // Eigen Matrix3f::inverse(): cofactors / det (column 0 expansion)
+  float c00 = m[4] * m[8] - m[5] * m[7];
+  float c10 = m[7] * m[2] - m[8] * m[1];
+  float c20 = m[1] * m[5] - m[2] * m[4];
+  float det = (c00 * m[0] + c10 * m[3]) + c20 * m[6];
+  float id = 1.0f / det;
+  o[0] = c00 * id; o[1] = c10 * id; o[2] = c20 * id;
+  o[3] = (m[5] * m[6] - m[3] * m[8]) * id;
+  o[4] = (m[8] * m[0] - m[6] * m[2]) * id;
+  o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  o[6] = (m[3] * m[7] - m[4] * m[6]) * id;
+  o[7] = (m[6] * m[1] - m[7] * m[0]) * id;
+  o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+__device__ __forceinline__ void mul3(const float* a, const float* b, float* o) {
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) o[r * 3 + c] = (a[r * 3] * b[c] + a[r * 3 + 1] * b[3 + c]) + a[r * 3 + 2] * b[6 + c];
+}
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) { return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+
+// Eigen SelfAdjointEigenSolver<Matrix3f>::computeDirect restated (closed-form roots + cross-product eigenvectors);
+// s: symmetric, row-major.  evec columns: V[r*3+c].
+__device__ __forceinline__ void eig3_extract_kernel(const float* m, float* res /*3*/, float* rep /*3 or null*/) {
+  int i0 = 0;
+  float best = fabsf(m[0]);
+  if (fabsf(m[4]) > best) { best = fabsf(m[4]); i0 = 1; }
+  if (fabsf(m[8]) > best) { best = fabsf(m[8]); i0 = 2; }
+  int i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
+  float3 r = make_float3(m[0 * 3 + i0], m[1 * 3 + i0], m[2 * 3 + i0]);
+  float3 a = make_float3(m[0 * 3 + i1], m[1 * 3 + i1], m[2 * 3 + i1]);
+  float3 b = make_float3(m[0 * 3 + i2], m[1 * 3 + i2], m[2 * 3 + i2]);
+  float3 c0 = cross3(r, a), c1 = cross3(r, b);
+  float n0 = (c0.x * c0.x + c0.y * c0.y) + c0.z * c0.z;
+  float n1 = (c1.x * c1.x + c1.y * c1.y) + c1.z * c1.z;
+  if (rep) { rep[0] = r.x; rep[1] = r.y; rep[2] = r.z; }
+  if (n0 > n1) {
+    float s = sqrtf(n0);
+    res[0] = c0.x / s; res[1] = c0.y / s; res[2] = c0.z / s;
+  } else {
+    float s = sqrtf(n1);
+    res[0] = c1.x / s; res[1] = c1.y / s; res[2] = c1.z / s;
+  }
+}
+
+__device__ void eig3_direct(const float* cov /*row-major sym*/, float* evals, float* V /*V[r*3+c], column c = eigenvector c*/) {
+  float s[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) s[i] = cov[i];
+  // selfadjointView<Lower>
+  s[1] = s[3]; s[2] = s[6]; s[5] = s[7];
+  float shift = ((s[0] + s[4]) + s[8]) / 3.0f;
+  s[0] -= shift; s[4] -= shift; s[8] -= shift;
+  float scale = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; i++) scale = fmaxf(scale, fabsf(s[i]));
+  if (scale > 0.0f) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) s[i] = s[i] / scale;
+  }
+  {  // computeRoots
+    const float s_inv3 = 1.0f / 3.0f;
+    const float s_sqrt3 = sqrtf(3.0f);
+    float c0 = s[0] * s[4] * s[8] + 2.0f * s[3] * s[6] * s[7] - s[0] * s[7] * s[7] - s[4] * s[6] * s[6] - s[8] * s[3] * s[3];
+    float c1 = s[0] * s[4] - s[3] * s[3] + s[0] * s[8] - s[6] * s[6] + s[4] * s[8] - s[7] * s[7];
+    float c2 = s[0] + s[4] + s[8];
+    float c2_over_3 = c2 * s_inv3;
+    float a_over_3 = fmaxf((c2 * c2_over_3 - c1) * s_inv3, 0.0f);
+    float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+    float q = fmaxf(a_over_3 * a_over_3 * a_over_3 - half_b * half_b, 0.0f);
+    float rho = sqrtf(a_over_3);
+    float theta = atan2f(sqrtf(q), half_b) * s_inv3;
+    float cos_theta = cosf(theta), sin_theta = sinf(theta);
+    evals[0] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+    evals[1] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+    evals[2] = c2_over_3 + 2.0f * rho * cos_theta;
+  }
+  const float eps = 1.1920929e-07f;
+  float v0[3], v1[3], v2[3];  // eigenvector columns
+  if ((evals[2] - evals[0]) <= eps) {
+    v0[0] = 1; v0[1] = 0; v0[2] = 0; v1[0] = 0; v1[1] = 1; v1[2] = 0; v2[0] = 0; v2[1] = 0; v2[2] = 1;
+  } else {
+    float d0 = evals[2] - evals[1];
+    float d1 = evals[1] - evals[0];
+    bool k_is_2 = d0 > d1;  // k = index of the most distinct eigenvalue, l = the other extreme
+    if (k_is_2) d0 = d1;
+    float ek = k_is_2 ? evals[2] : evals[0];
+    float el = k_is_2 ? evals[0] : evals[2];
+    float tmp[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) tmp[i] = s[i];
+    tmp[0] -= ek; tmp[4] -= ek; tmp[8] -= ek;
+    float vk[3], vl[3];
+    eig3_extract_kernel(tmp, vk, vl);
+    if (d0 <= 2.0f * eps * d1) {
+      float dot = (vk[0] * vl[0] + vk[1] * vl[1]) + vk[2] * vl[2];
+      float t0 = vl[0] - dot * vl[0], t1 = vl[1] - dot * vl[1], t2 = vl[2] - dot * vl[2];
+      float nn = sqrtf((t0 * t0 + t1 * t1) + t2 * t2);
+      if (nn > 0.0f) { vl[0] = t0 / nn; vl[1] = t1 / nn; vl[2] = t2 / nn; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; i++) tmp[i] = s[i];
+      tmp[0] -= el; tmp[4] -= el; tmp[8] -= el;
+      eig3_extract_kernel(tmp, vl, nullptr);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { v0[i] = k_is_2 ? vl[i] : vk[i]; v2[i] = k_is_2 ? vk[i] : vl[i]; }
+    float3 c = cross3(make_float3(v2[0], v2[1], v2[2]), make_float3(v0[0], v0[1], v0[2]));
+    float nn = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
+    if (nn > 0.0f) { v1[0] = c.x / nn; v1[1] = c.y / nn; v1[2] = c.z / nn; } else { v1[0] = c.x; v1[1] = c.y; v1[2] = c.z; }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; r++) { V[r * 3 + 0] = v0[r]; V[r * 3 + 1] = v1[r]; V[r * 3 + 2] = v2[r]; }
+#pragma unroll
+  for (int i = 0; i < 3; i++) evals[i] = evals[i] * scale + shift;
+}
+
+// covariance_regularization.cu: PLANE :105-116 (V diag(1e-3,1,1) V^-1), MIN_EIG :84-101, FROBENIUS :74-82.
+// c: row-major 3x3 in/out.
+__device__ void regularize_cov(float* c, int method) {
+  if (method == 3 /*PLANE*/ || method == 1 /*MIN_EIG*/) {
+    float ev[3], V[9], Vi[9], Vd[9];
+    eig3_direct(c, ev, V);
+    float l0 = 1e-3f, l1 = 1.0f, l2 = 1.0f;
+    if (method == 1) { l0 = fmaxf(1e-3f, ev[0]); l1 = fmaxf(1e-3f, ev[1]); l2 = fmaxf(1e-3f, ev[2]); }
+    inv3_general(V, Vi);
+#pragma unroll
+    for (int r = 0; r < 3; r++) { Vd[r * 3] = V[r * 3] * l0; Vd[r * 3 + 1] = V[r * 3 + 1] * l1; Vd[r * 3 + 2] = V[r * 3 + 2] * l2; }
+    mul3(Vd, Vi, c);
+  } else if (method == 4 /*FROBENIUS*/) {
+    float C[9], Ci[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) C[i] = c[i];
+    C[0] += 1e-3f; C[4] += 1e-3f; C[8] += 1e-3f;
+    inv3_general(C, Ci);
+    float nn = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; i++) nn += Ci[i] * Ci[i];
+    nn = sqrtf(nn);
+#pragma unroll
+    for (int i = 0; i < 9; i++) Ci[i] = Ci[i] / nn;
+    inv3_general(Ci, c);
+  }
+}
+
+__device__ __forceinline__ void store_cov_sym(const float* c /*row-major 3x3*/, float4* __restrict__ covA, float2* __restrict__ covB, int i) {
+  // the regularised matrix is symmetric up to float rounding of V*L*V^-1; the packed store keeps the mean of the
+  // two triangles (changes the final pose by ~1e-7 m)
+  covA[i] = make_float4(c[0], 0.5f * (c[1] + c[3]), 0.5f * (c[2] + c[6]), c[4]);
+  covB[i] = make_float2(0.5f * (c[5] + c[7]), c[8]);
+}
+
+// Stage 1b: covariance_estimation.cu:26-34 fused with the regulariser.
+__global__ void __launch_bounds__(128) k_covariance_knn(const float4* __restrict__ pts, const int* __restrict__ nbr, int n, int k, int method, float4* __restrict__ covA,
+                                                       float2* __restrict__ covB) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float mx = 0.f, my = 0.f, mz = 0.f;
+  float cxx = 0.f, cxy = 0.f, cxz = 0.f, cyy = 0.f, cyz = 0.f, czz = 0.f;
+  const int* row = nbr + (size_t)i * k;
+  for (int j = 0; j < k; j++) {
+    float4 p = pts[row[j]];
+    mx = __fadd_rn(mx, p.x); my = __fadd_rn(my, p.y); mz = __fadd_rn(mz, p.z);
+    cxx = __fmaf_rn(p.x, p.x, cxx); cxy = __fmaf_rn(p.x, p.y, cxy); cxz = __fmaf_rn(p.x, p.z, cxz);
+    cyy = __fmaf_rn(p.y, p.y, cyy); cyz = __fmaf_rn(p.y, p.z, cyz); czz = __fmaf_rn(p.z, p.z, czz);
+  }
+  float kf = (float)k;
+  mx = __fdiv_rn(mx, kf); my = __fdiv_rn(my, kf); mz = __fdiv_rn(mz, kf);
+  float c[9];
+  c[0] = __fmaf_rn(-mx, mx, __fdiv_rn(cxx, kf));
+  c[1] = c[3] = __fmaf_rn(-mx, my, __fdiv_rn(cxy, kf));
+  c[2] = c[6] = __fmaf_rn(-mx, mz, __fdiv_rn(cxz, kf));
+  c[4] = __fmaf_rn(-my, my, __fdiv_rn(cyy, kf));
+  c[5] = c[7] = __fmaf_rn(-my, mz, __fdiv_rn(cyz, kf));
+  c[8] = __fmaf_rn(-mz, mz, __fdiv_rn(czz, kf));
+  regularize_cov(c, method);
+  store_cov_sym(c, covA, covB, i);
+}
+
+// Stage 1b': covariance_estimation_rbf.cu:59-151.  One query per thread, all points streamed through shared memory in
+// blocks of 512 like the reference's per-block async transforms; partial sums per 512-block are folded in block order
+// (the reference's strided finalisation, :92-114).  The reference pads the cloud to a multiple of 512 with points at the
+// origin (:126-129) which pick up weight whenever the query is within max_dist of the origin -- reproduced.
+__global__ void __launch_bounds__(128) k_covariance_rbf(const float4* __restrict__ pts, int n, float exp_factor, float max_dist, int method, float4* __restrict__ covA,
+                                                       float2* __restrict__ covB) {
+  __shared__ float4 tile[kRbfBlock];
+  const int tid = threadIdx.x;
+  const int q = blockIdx.x * blockDim.x + tid;
+  const bool active = q < n;
+  float4 x = active ? pts[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float max_dist_sq = max_dist * max_dist;
+  float sw = 0.f, m[3] = {0.f, 0.f, 0.f}, c[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int nblocks = (n + kRbfBlock - 1) / kRbfBlock;
+  for (int b = 0; b < nblocks; b++) {
+    __syncthreads();
+    for (int j = tid; j < kRbfBlock; j += blockDim.x) {
+      int g = b * kRbfBlock + j;
+      tile[j] = g < n ? pts[g] : make_float4(0.f, 0.f, 0.f, 0.f);  // padding at the origin, :126-129
+    }
+    __syncthreads();
+    if (!active) continue;
+    float psw = 0.f, pm[3] = {0.f, 0.f, 0.f}, pc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < kRbfBlock; j++) {
+      float4 p = tile[j];
+      float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
+      float sq = (dx * dx + dy * dy) + dz * dz;
+      if (sq > max_dist_sq) continue;
+      float w = expf(-exp_factor * sq);
+      psw += w;
+      float wx = w * p.x, wy = w * p.y, wz = w * p.z;
+      pm[0] += wx; pm[1] += wy; pm[2] += wz;
+      pc[0] += wx * p.x; pc[1] += wx * p.y; pc[2] += wx * p.z; pc[3] += wy * p.y; pc[4] += wy * p.z; pc[5] += wz * p.z;
+    }
+    sw += psw;
+#pragma unroll
+    for (int d = 0; d < 3; d++) m[d] += pm[d];
+#pragma unroll
+    for (int d = 0; d < 6; d++) c[d] += pc[d];
+  }
+  if (!active) return;
+  // NormalDistribution::finalize :47-53:  mean = sum/sw ; cov = (cov - mean*sum^T)/sw
+  float mean[3] = {m[0] / sw, m[1] / sw, m[2] / sw};
+  float cc[9];
+  cc[0] = (c[0] - mean[0] * m[0]) / sw; cc[1] = (c[1] - mean[0] * m[1]) / sw; cc[2] = (c[2] - mean[0] * m[2]) / sw;
+  cc[3] = (c[1] - mean[1] * m[0]) / sw; cc[4] = (c[3] - mean[1] * m[1]) / sw; cc[5] = (c[4] - mean[1] * m[2]) / sw;
+  cc[6] = (c[2] - mean[2] * m[0]) / sw; cc[7] = (c[4] - mean[2] * m[1]) / sw; cc[8] = (c[5] - mean[2] * m[2]) / sw;
+  regularize_cov(cc, method);
+  store_cov_sym(cc, covA, covB, q);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stage 2: voxel map build (gaussian_voxelmap.cu:21-58, 61-73, 76-120, 158-176, 258-289)
+//
+// The reference resolves slot ownership by atomicCAS arrival order.  Here a contended slot goes to the voxel with
+// the lexicographically smaller coordinate and the loser keeps probing (priority linear probing): the final table
+// is exactly what serial first-come-first-served insertion of the distinct voxels in lexicographic order produces,
+// independent of thread timing -- the order the oracle uses.  slots[] holds a representative point index per voxel.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_voxel_coords(const float4* __restrict__ pts, int n, float res, int4* __restrict__ coords) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  coords[i] = make_int4(voxel_coord1(p.x, res), voxel_coord1(p.y, res), voxel_coord1(p.z, res), 0);
+}
+
+__global__ void k_fill_i32(int* __restrict__ p, int v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__device__ __forceinline__ bool coord_eq(int4 a, int4 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+__device__ __forceinline__ bool coord_less(int4 a, int4 b) {
+  if (a.x != b.x) return a.x < b.x;
+  if (a.y != b.y) return a.y < b.y;
+  return a.z < b.z;
+}
+
+__global__ void k_table_insert(const int4* __restrict__ coords, int n, int* slots, unsigned mask, int max_scan) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int cur = i;
+  int4 cc = coords[i];
+  unsigned pos = (unsigned)(vector3i_hash(cc.x, cc.y, cc.z) & mask);
+  int dist = 0;
+  while (dist < max_scan) {
+    int r = *reinterpret_cast<volatile int*>(&slots[pos]);
+    if (r < 0) {
+      int old = atomicCAS(&slots[pos], -1, cur);
+      if (old < 0) return;  // claimed an empty slot
+      r = old;
+    }
+    int4 cr = coords[r];
+    if (coord_eq(cr, cc)) return;  // voxel already present
+    if (coord_less(cc, cr)) {      // we outrank the resident: take the slot, carry the resident onward
+      int old = atomicCAS(&slots[pos], r, cur);
+      if (old != r) continue;      // slot changed under us: look again
+      cur = r;
+      cc = cr;
+      unsigned home = (unsigned)(vector3i_hash(cc.x, cc.y, cc.z) & mask);
+      dist = (int)((pos - home) & mask);
+    }
+    pos = (pos + 1) & mask;
+    dist++;
+  }
+  // fell off the 10-probe window: this voxel is dropped from the map (gaussian_voxelmap.cu:57)
+}
+
+// per point: find the slot of its voxel (stop at first empty like find_voxel_correspondences.cu:43-45) and count failures
+__global__ void k_table_lookup_points(const int4* __restrict__ coords, int n, const int* __restrict__ slots, unsigned mask, int max_scan, int* __restrict__ slot_of_point,
+                                      int* __restrict__ fail_counter) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 c = coords[i];
+  unsigned pos = (unsigned)(vector3i_hash(c.x, c.y, c.z) & mask);
+  int found = -1;
+  for (int s = 0; s < max_scan; s++) {
+    int r = slots[pos];
+    if (r < 0) break;
+    if (coord_eq(coords[r], c)) { found = (int)pos; break; }
+    pos = (pos + 1) & mask;
+  }
+  slot_of_point[i] = found;
+  if (found < 0) atomicAdd(fail_counter, 1);
+}
+
+// voxel id = rank of the slot among occupied slots; buckets = {coord, id} or {0,0,0,-1} (voxel_coord_select_kernel :61-73).
+// Single block, chunked inclusive scan with carry.
+__global__ void __launch_bounds__(1024) k_table_assign_ids(const int4* __restrict__ coords, const int* __restrict__ slots, int num_buckets, int4* __restrict__ buckets,
+                                                          int* __restrict__ num_voxels) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < num_buckets; base += 1024) {
+    int b = base + tid;
+    int r = b < num_buckets ? slots[b] : -1;
+    int flag = r >= 0 ? 1 : 0;
+    int v = flag;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) warp_sums[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    int prefix = carry + (wid > 0 ? warp_sums[wid - 1] : 0) + v - flag;  // exclusive
+    if (b < num_buckets) {
+      if (flag) {
+        int4 c = coords[r];
+        buckets[b] = make_int4(c.x, c.y, c.z, prefix);
+      } else {
+        buckets[b] = make_int4(0, 0, 0, -1);
+      }
+    }
+    __syncthreads();
+    if (tid == 1023) carry = prefix + flag;
+    __syncthreads();
+  }
+  if (tid == 0) *num_voxels = carry;
+}
+
+// accumulate_points_kernel :76-120 with double accumulators (the reference uses float atomicAdd in arrival order;
+// double sums rounded once make the result independent of the order to float precision).  sums: [V][10] doubles
+// (mean 3, cov 6 packed, spare), counts: [V].
+__global__ void k_voxel_accumulate(const float4* __restrict__ pts, const float4* __restrict__ covA, const float2* __restrict__ covB, int n, const int* __restrict__ slot_of_point,
+                                   const int4* __restrict__ buckets, double* __restrict__ sums, int* __restrict__ counts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int s = slot_of_point[i];
+  if (s < 0) return;
+  int id = buckets[s].w;
+  float4 p = pts[i];
+  float4 a = covA[i];
+  float2 b = covB[i];
+  double* d = sums + (size_t)id * 10;
+  atomicAdd(&counts[id], 1);
+  atomicAdd(d + 0, (double)p.x); atomicAdd(d + 1, (double)p.y); atomicAdd(d + 2, (double)p.z);
+  atomicAdd(d + 3, (double)a.x); atomicAdd(d + 4, (double)a.y); atomicAdd(d + 5, (double)a.z);
+  atomicAdd(d + 6, (double)a.w); atomicAdd(d + 7, (double)b.x); atomicAdd(d + 8, (double)b.y);
+}
+
+__global__ void k_voxel_finalize(const double* __restrict__ sums, const int* __restrict__ counts, int nv, VoxelRec* __restrict__ vox) {  // :158-176
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  int c = counts[v];
+  double inv = 1.0 / (double)c;
+  const double* d = sums + (size_t)v * 10;
+  VoxelRec r;
+  r.mean_n = make_float4((float)(d[0] * inv), (float)(d[1] * inv), (float)(d[2] * inv), __int_as_float(c));
+  r.c0 = make_float4((float)(d[3] * inv), (float)(d[4] * inv), (float)(d[5] * inv), (float)(d[6] * inv));
+  r.c1 = make_float4((float)(d[7] * inv), (float)(d[8] * inv), 0.f, 0.f);
+  vox[v] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stage 2b + 3 fused: per source point, transform by the linearisation pose, probe the neighbour voxels
+// (find_voxel_correspondences.cu:32-60), and accumulate the Mahalanobis residual and Jacobian terms
+// (compute_derivatives.cu:50-92 / :105-135) without materialising the correspondence list.
+//   J = [skew(p') | -I] depends on the point only, so  sum_c w J^T M_c J = J^T (sum_c w M_c) J : the 3x3 sums
+//   Msum = sum w M_c and v = sum w M_c e_c are formed per point and J is applied once.
+// Per-block partials (double) are folded by the last block in a fixed order -> bitwise reproducible H, b, err.
+// ---------------------------------------------------------------------------------------------------------------
+struct LinArgs {
+  const float4* pts;
+  const float4* covA;
+  const float2* covB;
+  int n;
+  const int4* buckets;
+  unsigned mask;
+  int max_scan;
+  const VoxelRec* vox;
+  const int4* offsets;  // generic mode
+  int n_off;
+  float res;
+  Pose Tlin, Teval;
+  double* partials;       // [gridDim.x][kLinValues]
+  unsigned int* ticket;   // zero before first launch; reset by the last block
+  double* out;            // [43]: err, H (36, column-major), b (6)
+};
+
+__device__ __forceinline__ int lookup_voxel(const int4* __restrict__ buckets, unsigned mask, int max_scan, uint64_t h, int cx, int cy, int cz) {
+  unsigned pos = (unsigned)(h & mask);
+  for (int s = 0; s < max_scan; s++) {
+    int4 b = __ldg(&buckets[pos]);
+    if (b.w < 0) return -1;
+    if (b.x == cx && b.y == cy && b.z == cz) return b.w;
+    pos = (pos + 1) & mask;
+  }
+  return -1;
+}
+
+template <bool WANT_H>
+struct PointAcc {
+  float m[6];  // sum w*M  (xx xy xz yy yz zz)
+  float v[3];  // sum w*M*e
+  float err;
+};
+
+template <bool WANT_H>
+__device__ __forceinline__ void accumulate_voxel(const VoxelRec* __restrict__ vox, int id, const float* rcr, float3 pe, PointAcc<WANT_H>& acc) {
+  const float4* vr = reinterpret_cast<const float4*>(vox + id);
+  float4 mn = __ldg(vr), c0 = __ldg(vr + 1), c1 = __ldg(vr + 2);
+  int np = __float_as_int(mn.w);
+  if (WANT_H && np <= 0) return;  // compute_derivatives.cu:62-64
+  // S = C_B + R C_A R^T (symmetric), M = S^-1 by cofactors (Eigen Matrix3f::inverse)
+  float a = c0.x + rcr[0], b = c0.y + rcr[1], c = c0.z + rcr[2], d = c0.w + rcr[3], e = c1.x + rcr[4], f = c1.y + rcr[5];
+  float k00 = d * f - e * e, k01 = c * e - b * f, k02 = b * e - c * d;
+  float det = (a * k00 + b * k01) + c * k02;
+  float id_ = 1.0f / det;
+  float m00 = k00 * id_, m01 = k01 * id_, m02 = k02 * id_;
+  float m11 = (a * f - c * c) * id_, m12 = (b * c - a * e) * id_, m22 = (a * d - b * b) * id_;
+  float w = sqrtf((float)np);
+  float ex = mn.x - pe.x, ey = mn.y - pe.y, ez = mn.z - pe.z;
+  float mex = (m00 * ex + m01 * ey) + m02 * ez;
+  float mey = (m01 * ex + m11 * ey) + m12 * ez;
+  float mez = (m02 * ex + m12 * ey) + m22 * ez;
+  acc.err += w * ((ex * mex + ey * mey) + ez * mez);
+  if (WANT_H) {
+    acc.m[0] += w * m00; acc.m[1] += w * m01; acc.m[2] += w * m02; acc.m[3] += w * m11; acc.m[4] += w * m12; acc.m[5] += w * m22;
+    acc.v[0] += w * mex; acc.v[1] += w * mey; acc.v[2] += w * mez;
+  }
+}
+
+// MODE: 0 = offsets from memory (DIRECT_RADIUS or anything), 1 / 7 / 27 = the reference's fixed tables generated in
+// registers, for 27 with the x/y prefixes of the hash shared between neighbours.
+template <int MODE, bool WANT_H>
+__global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
+  constexpr int NV = WANT_H ? kLinValues : 1;
+  float sum[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) sum[i] = 0.f;
+
+  const Pose Tl = a.Tlin, Te = a.Teval;
+  for (int i = blockIdx.x * kLinThreads + threadIdx.x; i < a.n; i += gridDim.x * kLinThreads) {
+    float4 p = a.pts[i];
+    float4 ca = a.covA[i];
+    float2 cb = a.covB[i];
+    float3 pl = transform_point(Tl, p.x, p.y, p.z);
+    float3 pe = transform_point(Te, p.x, p.y, p.z);
+    // RCR = R_lin C_A R_lin^T  (compute_derivatives.cu:75), symmetric-packed
+    float rcr[6];
+    {
+      const float* R = Tl.r;
+      float t[9];  // T = R*C
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        t[r * 3 + 0] = (R[r * 3] * ca.x + R[r * 3 + 1] * ca.y) + R[r * 3 + 2] * ca.z;
+        t[r * 3 + 1] = (R[r * 3] * ca.y + R[r * 3 + 1] * ca.w) + R[r * 3 + 2] * cb.x;
+        t[r * 3 + 2] = (R[r * 3] * ca.z + R[r * 3 + 1] * cb.x) + R[r * 3 + 2] * cb.y;
+      }
+      rcr[0] = (t[0] * R[0] + t[1] * R[1]) + t[2] * R[2];
+      rcr[1] = (t[0] * R[3] + t[1] * R[4]) + t[2] * R[5];
+      rcr[2] = (t[0] * R[6] + t[1] * R[7]) + t[2] * R[8];
+      rcr[3] = (t[3] * R[3] + t[4] * R[4]) + t[5] * R[5];
+      rcr[4] = (t[3] * R[6] + t[4] * R[7]) + t[5] * R[8];
+      rcr[5] = (t[6] * R[6] + t[7] * R[7]) + t[8] * R[8];
+    }
+    const int bx = voxel_coord1(pl.x, a.res), by = voxel_coord1(pl.y, a.res), bz = voxel_coord1(pl.z, a.res);
+    PointAcc<WANT_H> acc;
+#pragma unroll
+    for (int q = 0; q < 6; q++) acc.m[q] = 0.f;
+    acc.v[0] = acc.v[1] = acc.v[2] = 0.f;
+    acc.err = 0.f;
+
+    if (MODE == 27) {
+      uint64_t kx[3], ky[3], kz[3];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        kx[d] = hash_mix((uint64_t)(int64_t)(bx + d - 1));
+        ky[d] = hash_mix((uint64_t)(int64_t)(by + d - 1));
+        kz[d] = hash_mix((uint64_t)(int64_t)(bz + d - 1));
+      }
+#pragma unroll
+      for (int ix = 0; ix < 3; ix++) {
+        uint64_t hx = hash_fold(0, kx[ix]);
+#pragma unroll
+        for (int iy = 0; iy < 3; iy++) {
+          uint64_t hy = hash_fold(hx, ky[iy]);
+#pragma unroll
+          for (int iz = 0; iz < 3; iz++) {
+            uint64_t h = hash_fold(hy, kz[iz]);
+            int id = lookup_voxel(a.buckets, a.mask, a.max_scan, h, bx + ix - 1, by + iy - 1, bz + iz - 1);
+            if (id >= 0) accumulate_voxel<WANT_H>(a.vox, id, rcr, pe, acc);
+          }
+        }
+      }
+    } else if (MODE == 7) {
+      const int ox[7] = {0, 1, -1, 0, 0, 0, 0}, oy[7] = {0, 0, 0, 1, -1, 0, 0}, oz[7] = {0, 0, 0, 0, 0, 1, -1};
+#pragma unroll
+      for (int o = 0; o < 7; o++) {
+        int cx = bx + ox[o], cy = by + oy[o], cz = bz + oz[o];
+        int id = lookup_voxel(a.buckets, a.mask, a.max_scan, vector3i_hash(cx, cy, cz), cx, cy, cz);
+        if (id >= 0) accumulate_voxel<WANT_H>(a.vox, id, rcr, pe, acc);
+      }
+    } else if (MODE == 1) {
+      int id = lookup_voxel(a.buckets, a.mask, a.max_scan, vector3i_hash(bx, by, bz), bx, by, bz);
+      if (id >= 0) accumulate_voxel<WANT_H>(a.vox, id, rcr, pe, acc);
+    } else {
+      for (int o = 0; o < a.n_off; o++) {
+        int4 off = __ldg(&a.offsets[o]);
+        int cx = bx + off.x, cy = by + off.y, cz = bz + off.z;
+        int id = lookup_voxel(a.buckets, a.mask, a.max_scan, vector3i_hash(cx, cy, cz), cx, cy, cz);
+        if (id >= 0) accumulate_voxel<WANT_H>(a.vox, id, rcr, pe, acc);
+      }
+    }
+
+    if (WANT_H) {
+      // B = S*Msum (3x3), A = -B*S, with S = skew(pe);  H = [[A, B],[B^T, Msum]],  b = [-(pe x v); -v]
+      const float* M = acc.m;  // xx xy xz yy yz zz
+      float Mf[9] = {M[0], M[1], M[2], M[1], M[3], M[4], M[2], M[4], M[5]};
+      float B[9];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        B[0 * 3 + j] = pe.y * Mf[2 * 3 + j] - pe.z * Mf[1 * 3 + j];
+        B[1 * 3 + j] = pe.z * Mf[0 * 3 + j] - pe.x * Mf[2 * 3 + j];
+        B[2 * 3 + j] = pe.x * Mf[1 * 3 + j] - pe.y * Mf[0 * 3 + j];
+      }
+      // (B*S)[i][0] = B[i][1]*pz - B[i][2]*py ; [i][1] = -B[i][0]*pz + B[i][2]*px ; [i][2] = B[i][0]*py - B[i][1]*px
+      float A00 = -(B[1] * pe.z - B[2] * pe.y);
+      float A01 = -(-B[0] * pe.z + B[2] * pe.x);
+      float A02 = -(B[0] * pe.y - B[1] * pe.x);
+      float A11 = -(-B[3] * pe.z + B[5] * pe.x);
+      float A12 = -(B[3] * pe.y - B[4] * pe.x);
+      float A22 = -(B[6] * pe.y - B[7] * pe.x);
+      sum[0] += acc.err;
+      sum[1] += A00; sum[2] += A01; sum[3] += A02; sum[4] += A11; sum[5] += A12; sum[6] += A22;
+#pragma unroll
+      for (int j = 0; j < 9; j++) sum[7 + j] += B[j];
+#pragma unroll
+      for (int j = 0; j < 6; j++) sum[16 + j] += M[j];
+      sum[22] += -(pe.y * acc.v[2] - pe.z * acc.v[1]);
+      sum[23] += -(pe.z * acc.v[0] - pe.x * acc.v[2]);
+      sum[24] += -(pe.x * acc.v[1] - pe.y * acc.v[0]);
+      sum[25] += -acc.v[0]; sum[26] += -acc.v[1]; sum[27] += -acc.v[2];
+    } else {
+      sum[0] += acc.err;
+    }
+  }
+
+  // ---- block reduction: warp shuffles (float) -> shared (double) -> per-block partial ----
+  __shared__ double sh[kLinThreads / 32][kLinValues];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    float v = sum[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[wid][i] = (double)v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kLinThreads / 32; w++) s += sh[w][threadIdx.x];
+    a.partials[(size_t)blockIdx.x * kLinValues + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(a.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // ---- last block: fold the per-block partials in block order (4 interleaved chains per value) ----
+  __shared__ double fin[4][kLinValues];
+  {
+    const int v = threadIdx.x & 31, chain = threadIdx.x >> 5;  // kLinThreads == 128 -> 4 chains
+    if (v < NV) {
+      double s = 0.0;
+      const volatile double* part = a.partials;
+      for (unsigned b = chain; b < gridDim.x; b += 4) s += part[(size_t)b * kLinValues + v];
+      fin[chain][v] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = ((fin[0][threadIdx.x] + fin[1][threadIdx.x]) + fin[2][threadIdx.x]) + fin[3][threadIdx.x];
+    fin[0][threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double* out = a.out;
+    out[0] = fin[0][0];
+    if (WANT_H) {
+      const double* s = fin[0];
+      double H[36];
+      // A (rows/cols 0..2)
+      H[0 * 6 + 0] = s[1]; H[1 * 6 + 0] = H[0 * 6 + 1] = s[2]; H[2 * 6 + 0] = H[0 * 6 + 2] = s[3];
+      H[1 * 6 + 1] = s[4]; H[2 * 6 + 1] = H[1 * 6 + 2] = s[5]; H[2 * 6 + 2] = s[6];
+      // B: H(r, 3+c) = B[r][c] (column-major index (3+c)*6 + r) and its transpose
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+          H[(3 + c) * 6 + r] = s[7 + r * 3 + c];
+          H[r * 6 + (3 + c)] = s[7 + r * 3 + c];
+        }
+      // M (rows/cols 3..5)
+      H[3 * 6 + 3] = s[16]; H[4 * 6 + 3] = H[3 * 6 + 4] = s[17]; H[5 * 6 + 3] = H[3 * 6 + 5] = s[18];
+      H[4 * 6 + 4] = s[19]; H[5 * 6 + 4] = H[4 * 6 + 5] = s[20]; H[5 * 6 + 5] = s[21];
+      for (int j = 0; j < 36; j++) out[1 + j] = H[j];
+      for (int j = 0; j < 6; j++) out[37 + j] = s[22 + j];
+    }
+    *a.ticket = 0u;
+  }
+}
+
+// Materialise the reference's correspondence list for the getter (fast_vgicp_cuda.cu:221-225): dense [n_off][n] voxel ids,
+// compacted on the host in offset-major / point-minor order.
+__global__ void k_correspondence_ids(const float4* __restrict__ pts, int n, const int4* __restrict__ buckets, unsigned mask, int max_scan, const int4* __restrict__ offsets, int n_off,
+                                     float res, const Pose Tlin, int* __restrict__ ids) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  float3 pl = transform_point(Tlin, p.x, p.y, p.z);
+  int bx = voxel_coord1(pl.x, res), by = voxel_coord1(pl.y, res), bz = voxel_coord1(pl.z, res);
+  for (int o = 0; o < n_off; o++) {
+    int4 off = offsets[o];
+    int cx = bx + off.x, cy = by + off.y, cz = bz + off.z;
+    ids[(size_t)o * n + i] = lookup_voxel(buckets, mask, max_scan, vector3i_hash(cx, cy, cz), cx, cy, cz);
+  }
+}
+
+// pcl::transformPointCloud (lsq_registration_impl.hpp:78): out = T * p, written back in the caller's stride
+__global__ void k_transform_points(const float4* __restrict__ pts, int n, const Pose T, unsigned char* __restrict__ out, size_t stride) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  float3 o = transform_point(T, p.x, p.y, p.z);
+  float* dst = reinterpret_cast<float*>(out + (size_t)i * stride);
+  dst[0] = o.x; dst[1] = o.y; dst[2] = o.z;
+}
+
+}  // namespace vgicp

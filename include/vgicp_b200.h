@@ -1,0 +1,160 @@
+/*
+ * vgicp_b200.h -- C ABI of libvgicp_b200.so, the Blackwell (sm_100a) VGICP registration core.
+ *
+ * This is the drop-in seam for fast_gicp's device core: every function below replaces one member of
+ * fast_gicp::cuda::FastVGICPCudaCore (reference include/fast_gicp/cuda/fast_vgicp_cuda.cuh:28-92, implemented in
+ * src/fast_gicp/cuda/fast_vgicp_cuda.cu:18-284) and is called from exactly the places
+ * include/fast_gicp/gicp/impl/fast_vgicp_cuda_impl.hpp calls that member.  Plain pointers and sizes only: no
+ * Eigen, thrust, PCL or torch types cross this boundary.
+ *
+ * Conventions
+ *   - every call returns a vgicp_status (0 = OK); it never throws, asserts or aborts (the reference asserts /
+ *     abort()s, fast_vgicp_cuda.cu:46-48,128,139,...).  vgicp_last_error() gives the message of the last failure.
+ *   - one handle <-> one FastVGICPCudaCore: owns one CUDA stream and all device buffers; calls on one handle are
+ *     stream-ordered; a handle must not be used from two host threads at once (same as the reference).
+ *   - clouds: float32 xyz, `stride_bytes` between consecutive points (12 for packed Eigen::Vector3f, 16 for
+ *     pcl::PointXYZ, 32 for pcl::PointXYZI ...).  Inputs are copied; the caller keeps ownership.
+ *   - poses: 16 doubles, column-major 4x4 == Eigen::Isometry3d::data().
+ *   - 3x3 matrices returned to the host: 9 floats column-major == Eigen::Matrix3f::data() (36 B), as in the
+ *     reference's get_*_covariances / get_voxel_covs.
+ *   - H: 36 doubles column-major 6x6 == Eigen::Matrix<double,6,6>::data(); b: 6 doubles.
+ *   - enums are passed as int with the reference's numeric order (include/fast_gicp/gicp/gicp_settings.hpp:6-10).
+ */
+#ifndef VGICP_B200_H
+#define VGICP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VGICP_API __attribute__((visibility("default")))
+#else
+#define VGICP_API
+#endif
+
+typedef struct vgicp_context* vgicp_handle;
+
+typedef enum {
+  VGICP_OK = 0,
+  VGICP_ERR_INVALID_ARGUMENT = 1, /* null pointer, bad enum, k out of range, size mismatch */
+  VGICP_ERR_BAD_STATE = 2,        /* a prerequisite call is missing (e.g. covariances before the cloud) */
+  VGICP_ERR_CUDA = 3,             /* a CUDA runtime call failed; message has the cudaError string */
+  VGICP_ERR_UNSUPPORTED = 4,      /* regularisation method not implemented on the GPU path (as in the reference) */
+  VGICP_ERR_NO_DEVICE = 5,        /* no CUDA device / kernel image not loadable on this GPU (needs sm_100a) */
+  VGICP_ERR_COMM = 6              /* multi-GPU exchange failed */
+} vgicp_status;
+
+/* fast_gicp::RegularizationMethod, gicp_settings.hpp:6 */
+enum { VGICP_REG_NONE = 0, VGICP_REG_MIN_EIG = 1, VGICP_REG_NORMALIZED_MIN_EIG = 2, VGICP_REG_PLANE = 3, VGICP_REG_FROBENIUS = 4 };
+/* fast_gicp::NeighborSearchMethod, gicp_settings.hpp:8 */
+enum { VGICP_DIRECT27 = 0, VGICP_DIRECT7 = 1, VGICP_DIRECT1 = 2, VGICP_DIRECT_RADIUS = 3 };
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------ */
+/* FastVGICPCudaCore::FastVGICPCudaCore()  fast_vgicp_cuda.cu:18-30.  `device` = CUDA ordinal (the reference uses the
+ * current device); defaults installed: resolution 1.0, kernel_width 0.25, kernel_max_dist 3.0, offsets = DIRECT1. */
+VGICP_API int vgicp_create(int device, vgicp_handle* out);
+VGICP_API int vgicp_destroy(vgicp_handle h);
+VGICP_API const char* vgicp_last_error(vgicp_handle h); /* valid until the next call on h; "" if none */
+VGICP_API const char* vgicp_version(void);
+
+/* ---- settings ------------------------------------------------------------------------------------------------ */
+VGICP_API int vgicp_set_resolution(vgicp_handle h, double resolution);                              /* :32-34 */
+VGICP_API int vgicp_set_kernel_params(vgicp_handle h, double kernel_width, double kernel_max_dist); /* :36-39 */
+VGICP_API int vgicp_set_neighbor_search_method(vgicp_handle h, int method, double radius);          /* :41-95 */
+
+/* ---- clouds -------------------------------------------------------------------------------------------------- */
+VGICP_API int vgicp_set_source_cloud(vgicp_handle h, const float* xyz, size_t n, size_t stride_bytes); /* :109-116 */
+VGICP_API int vgicp_set_target_cloud(vgicp_handle h, const float* xyz, size_t n, size_t stride_bytes); /* :118-125 */
+VGICP_API int vgicp_swap_source_and_target(vgicp_handle h); /* :97-107: swaps points/neighbours/covariances and, when the
+                                                               new target has covariances, rebuilds the voxel map */
+
+/* ---- stage 1: neighbours + covariances ----------------------------------------------------------------------- */
+/* set_{source,target}_neighbors :127-147 -- host-computed k-NN indices, row i = neighbours of point i; n_times_k must
+ * equal k * cloud size (the reference asserts it). */
+VGICP_API int vgicp_set_source_neighbors(vgicp_handle h, int k, const int* indices, size_t n_times_k);
+VGICP_API int vgicp_set_target_neighbors(vgicp_handle h, int k, const int* indices, size_t n_times_k);
+/* find_{source,target}_neighbors :155-181 -- exact k-NN of every point within its own cloud (self included) on the GPU.
+ * Rows come out ascending in (squared distance, index) -- the kd-tree order; the reference's brute-force mode leaves heap
+ * order, same set.  1 <= k <= min(n, 64). */
+VGICP_API int vgicp_find_source_neighbors(vgicp_handle h, int k);
+VGICP_API int vgicp_find_target_neighbors(vgicp_handle h, int k);
+/* calculate_{source,target}_covariances :183-203 -- covariance_estimation + covariance_regularization(method).
+ * NONE leaves the raw covariance; NORMALIZED_MIN_EIG is not implemented on the reference's GPU path (it prints an error and
+ * leaves the raw covariance): same here, with VGICP_ERR_UNSUPPORTED returned after the raw covariances are in place. */
+VGICP_API int vgicp_calculate_source_covariances(vgicp_handle h, int regularization_method);
+VGICP_API int vgicp_calculate_target_covariances(vgicp_handle h, int regularization_method);
+/* calculate_{source,target}_covariances_rbf :205-219 -- kernel-weighted covariances, w = exp(-kernel_width * d^2), d <= max_dist */
+VGICP_API int vgicp_calculate_source_covariances_rbf(vgicp_handle h, int regularization_method);
+VGICP_API int vgicp_calculate_target_covariances_rbf(vgicp_handle h, int regularization_method);
+/* get_{source,target}_covariances :245-255 -- out9: n x 9 floats */
+VGICP_API int vgicp_get_source_covariances(vgicp_handle h, float* out9, size_t capacity_points);
+VGICP_API int vgicp_get_target_covariances(vgicp_handle h, float* out9, size_t capacity_points);
+/* public members source_neighbors / target_neighbors (fast_vgicp_cuda.cuh:80-81) read back: n x k ints */
+VGICP_API int vgicp_get_source_neighbors(vgicp_handle h, int* out, size_t capacity_ints, int* k_out);
+VGICP_API int vgicp_get_target_neighbors(vgicp_handle h, int* out, size_t capacity_ints, int* k_out);
+VGICP_API int vgicp_get_num_source_points(vgicp_handle h, size_t* n);
+VGICP_API int vgicp_get_num_target_points(vgicp_handle h, size_t* n);
+
+/* ---- stage 2: Gaussian voxel map ----------------------------------------------------------------------------- */
+/* create_target_voxelmap :257-263 (GaussianVoxelMap::create_voxelmap(points, covs), gaussian_voxelmap.cu:233-289).
+ * As in the reference the map object keeps the resolution it was first created with. */
+VGICP_API int vgicp_create_target_voxelmap(vgicp_handle h);
+VGICP_API int vgicp_get_num_voxels(vgicp_handle h, int* num_voxels);   /* voxelmap_info.num_voxels */
+VGICP_API int vgicp_get_num_buckets(vgicp_handle h, int* num_buckets); /* voxelmap_info.num_buckets */
+VGICP_API int vgicp_get_voxel_num_points(vgicp_handle h, int* out, size_t capacity_voxels); /* :227-231 */
+VGICP_API int vgicp_get_voxel_means(vgicp_handle h, float* out3, size_t capacity_voxels);   /* :233-237 */
+VGICP_API int vgicp_get_voxel_covs(vgicp_handle h, float* out9, size_t capacity_voxels);    /* :239-243 */
+/* public member voxelmap->buckets (gaussian_voxelmap.cuh:32): per bucket {coord xyz, voxel id}; empty = {0,0,0,-1} */
+VGICP_API int vgicp_get_voxel_buckets(vgicp_handle h, int* coords3, int* ids, size_t capacity_buckets);
+
+/* ---- stage 2b + 3: correspondences and the linear system ----------------------------------------------------- */
+/* update_correspondences :265-274 -- fixes the linearisation pose (cast to float like the reference). */
+VGICP_API int vgicp_update_correspondences(vgicp_handle h, const double T[16]);
+/* get_voxel_correspondences :221-225 -- (source index, voxel id) pairs, offset-major / point-minor like the reference's list.
+ * Pass pairs=NULL to query the count. */
+VGICP_API int vgicp_get_voxel_correspondences(vgicp_handle h, int* pairs, size_t capacity_pairs, size_t* n_pairs);
+/* compute_error :276-284 -> compute_derivatives (compute_derivatives.cu:151-184).  H36 and b6 may both be NULL
+ * (error only).  *err receives the return value of the reference's compute_error. */
+VGICP_API int vgicp_compute_error(vgicp_handle h, const double T[16], double* H36, double* b6, double* err);
+
+/* ---- extensions (not in the reference core) ------------------------------------------------------------------ */
+/* LsqRegistration defaults, include/fast_gicp/gicp/impl/lsq_registration_impl.hpp:9-22 */
+typedef struct {
+  int max_iterations;            /* 64 */
+  double rotation_epsilon;       /* 2e-3 */
+  double transformation_epsilon; /* 5e-4 */
+  int use_gauss_newton;          /* 0: Levenberg-Marquardt (default), 1: Gauss-Newton */
+  int lm_max_iterations;         /* 10 */
+  double lm_init_lambda_factor;  /* 1e-9 */
+} vgicp_lsq_params;
+
+typedef struct {
+  double T[16];        /* final pose x0 (double, before the reference's cast to float) */
+  double H[36];        /* final_hessian_ */
+  int nr_iterations;   /* nr_iterations_ */
+  int converged;       /* converged_ */
+  int n_linearize;     /* evaluations with H,b */
+  int n_compute_error; /* error-only evaluations */
+  int lm_failed;       /* 1 when the reference would print "lm not converged!!" */
+} vgicp_align_result;
+
+VGICP_API void vgicp_lsq_default_params(vgicp_lsq_params* p);
+/* Whole LsqRegistration::computeTransformation loop (lsq_registration_impl.hpp:53-79,106-168) run device-resident:
+ * same linearize / compute_error evaluations, same LM logic in double, no host round trip per evaluation. */
+VGICP_API int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* params, vgicp_align_result* result);
+/* pcl::transformPointCloud of the source by T (lsq_registration_impl.hpp:78) on the device; out: n x stride floats */
+VGICP_API int vgicp_transform_source(vgicp_handle h, const double T[16], float* out_xyz, size_t capacity_points, size_t stride_bytes);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+VGICP_API int vgicp_get_launch_count(vgicp_handle h, uint64_t* launches);
+VGICP_API int vgicp_synchronize(vgicp_handle h);
+/* cudaStream_t of the handle as an integer, for CUDA-event timing on the launching stream */
+VGICP_API int vgicp_get_stream(vgicp_handle h, uint64_t* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGICP_B200_H */

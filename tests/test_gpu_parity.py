@@ -1,0 +1,340 @@
+"""GPU parity tests: the CUDA path (through the C ABI, fast_gicp_b200.core.Core) against the CPU oracle on the same inputs.
+
+Tolerances (north_star): voxel-hash values / coordinates / bucket indices bit-exact; final SE(3) within 1e-5 rad / 1e-4 m of
+the oracle; reference's own gate 0.05 m / 1 deg against data/relative.txt (src/test/gicp_test.cpp:147-201).
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import pose_error, random_pose
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-5    # rad, north_star
+TRANS_TOL = 1e-4  # m, north_star
+
+
+@pytest.fixture(scope="module")
+def core():
+    from fast_gicp_b200.core import Core
+
+    c = Core(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def prepared(pair02):
+    """Oracle products for the 0.2 m fixture pair (the reference's test inputs)."""
+    tgt, src = pair02
+    t_nbr = O.knn(tgt, 20, "kdtree")
+    s_nbr = O.knn(src, 20, "kdtree")
+    t_raw = O.covariances(tgt, t_nbr)
+    s_raw = O.covariances(src, s_nbr)
+    t_cov = O.regularize(t_raw, O.REG_PLANE)
+    s_cov = O.regularize(s_raw, O.REG_PLANE)
+    return dict(tgt=tgt, src=src, t_nbr=t_nbr, s_nbr=s_nbr, t_raw=t_raw, s_raw=s_raw, t_cov=t_cov, s_cov=s_cov)
+
+
+def sym(c9):
+    m = c9.reshape(-1, 3, 3)
+    return (0.5 * (m + m.transpose(0, 2, 1))).reshape(-1, 9)
+
+
+# ---------------------------------------------------------------------------------------------------------- stage 1
+def test_knn_matches_oracle_exactly(core, prepared):
+    """find_target_neighbors: exact k-NN, rows ascending in (d2, index) -- identical to the oracle (kd-tree and brute force)."""
+    core.set_target_cloud(prepared["tgt"])
+    core.find_target_neighbors(20)
+    got = core.get_target_neighbors()
+    assert got.shape == prepared["t_nbr"].shape
+    assert np.array_equal(got, prepared["t_nbr"])
+    assert np.array_equal(got[:, 0], np.arange(len(got)))  # self is neighbour 0 (H6)
+
+
+@pytest.mark.parametrize("k", [1, 7, 33, 64])
+def test_knn_other_k(core, k):
+    rng = np.random.default_rng(k)
+    pts = rng.uniform(-20, 20, size=(1500, 3)).astype(np.float32)
+    pts[100:110] = pts[100]  # duplicates: ties broken by index
+    core.set_source_cloud(pts)
+    core.find_source_neighbors(k)
+    assert np.array_equal(core.get_source_neighbors(), O.knn(pts, k, "bruteforce"))
+
+
+def test_raw_covariance_bit_exact(core, prepared):
+    """covariance_estimation.cu:26-34 (RegularizationMethod NONE leaves it raw): same fma sequence as the oracle -> bit-exact."""
+    core.set_target_cloud(prepared["tgt"])
+    core.set_target_neighbors(20, prepared["t_nbr"])
+    core.calculate_target_covariances(O.REG_NONE)
+    got = core.get_target_covariances()
+    assert np.array_equal(got, prepared["t_raw"])
+
+
+@pytest.mark.parametrize("method,tol", [(O.REG_PLANE, 3e-5), (O.REG_MIN_EIG, 3e-5), (O.REG_FROBENIUS, 3e-5)])
+def test_regularised_covariance(core, prepared, method, tol):
+    """Same closed-form eigen-solver on both sides; libm vs CUDA atan2f/cosf/sinf differ by ulps, and the GPU keeps the
+    symmetric part of V L V^-1."""
+    core.set_target_cloud(prepared["tgt"])
+    core.set_target_neighbors(20, prepared["t_nbr"])
+    core.calculate_target_covariances(method)
+    got = core.get_target_covariances()
+    want = sym(O.regularize(prepared["t_raw"], method))
+    scale = np.maximum(1.0, np.abs(want).max(axis=1, keepdims=True))
+    err = np.abs(got - want) / scale
+    # ill-conditioned neighbourhoods amplify ulp differences: allow a handful of outliers, none large
+    assert np.percentile(err, 99.9) < tol, np.percentile(err, 99.9)
+    assert err.max() < 5e-3, err.max()
+
+
+def test_plane_regularisation_identity(core, prepared):
+    """C_reg = I - 0.999 n n^T up to rounding: eigenvalues (1e-3, 1, 1)."""
+    core.set_source_cloud(prepared["src"])
+    core.set_source_neighbors(20, prepared["s_nbr"])
+    core.calculate_source_covariances(O.REG_PLANE)
+    got = core.get_source_covariances().reshape(-1, 3, 3).astype(np.float64)
+    w = np.linalg.eigvalsh(got)
+    assert np.abs(w[:, 0] - 1e-3).max() < 1e-3
+    assert np.abs(w[:, 1:] - 1.0).max() < 1e-3
+
+
+def test_normalized_min_eig_unsupported(core, prepared):
+    from fast_gicp_b200.core import ERR_UNSUPPORTED
+
+    core.set_source_cloud(prepared["src"])
+    core.set_source_neighbors(20, prepared["s_nbr"])
+    rc = core.calculate_source_covariances(O.REG_NORMALIZED_MIN_EIG)
+    assert rc == ERR_UNSUPPORTED  # reference prints "unimplemented ..." and leaves the raw covariance
+    assert np.array_equal(core.get_source_covariances(), prepared["s_raw"])
+
+
+# ---------------------------------------------------------------------------------------------------------- stage 2
+@pytest.mark.parametrize("res", [1.0, 0.5, 0.25])
+def test_voxelmap_table_bit_exact(prepared, res):
+    """calc_voxel_coord, vector3i_hash, bucket = (hash+i) % num_buckets, growth rule: table identical to the oracle's."""
+    from fast_gicp_b200.core import Core
+
+    c = Core(0)
+    c.set_resolution(res)
+    c.set_target_cloud(prepared["tgt"])
+    c.set_target_neighbors(20, prepared["t_nbr"])
+    c.calculate_target_covariances(O.REG_PLANE)
+    c.create_target_voxelmap()
+    vm = O.VoxelMap(prepared["tgt"], sym(prepared["t_cov"]).astype(np.float32), res, accum_double=True)
+    assert c.num_buckets() == vm.num_buckets
+    assert c.num_voxels() == vm.num_voxels
+    coords, ids = c.get_voxel_buckets()
+    assert np.array_equal(ids, vm.bucket_id)
+    assert np.array_equal(coords, vm.bucket_coord)
+    # every occupied bucket sits within 10 probes of its hash (bit-exact hash check on the device-built table)
+    occ = np.flatnonzero(ids >= 0)
+    h = O.hashes(coords[occ])
+    disp = (occ.astype(np.uint64) - (h % np.uint64(len(ids)))) % np.uint64(len(ids))
+    assert disp.max() < 10
+    assert np.array_equal(c.get_voxel_num_points(), vm.vox_n)
+    # means / covs: GPU accumulates in double and rounds once == oracle accum_double mode (GPU covariances differ by ulps)
+    assert np.abs(c.get_voxel_means() - vm.vox_mean).max() < 1e-5
+    cov_err = np.abs(c.get_voxel_covs() - vm.vox_cov).max(axis=1)  # single-point voxels inherit the per-point outliers
+    assert np.percentile(cov_err, 99.5) < 5e-5 and cov_err.max() < 5e-3, (np.percentile(cov_err, 99.5), cov_err.max())
+    # the reference's float accumulation (any order) stays within float rounding of it
+    vmf = O.VoxelMap(prepared["tgt"], sym(prepared["t_cov"]).astype(np.float32), res, accum_double=False)
+    assert np.abs(c.get_voxel_means() - vmf.vox_mean).max() < 2e-4
+    c.close()
+
+
+def test_voxelmap_growth_and_drops():
+    """Dense random cloud: the 8192-bucket table overflows, the map grows by doubling until <1% of points fail (Q5)."""
+    from fast_gicp_b200.core import Core
+
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(-40, 40, size=(60000, 3)).astype(np.float32)
+    cov = np.tile(np.eye(3, dtype=np.float32).reshape(9), (len(pts), 1))
+    nbr = np.tile(np.arange(1, dtype=np.int32), (len(pts), 1))
+    c = Core(0)
+    c.set_resolution(1.0)
+    c.set_target_cloud(pts)
+    c.set_target_neighbors(1, nbr)  # k=1 -> zero raw covariance, NONE keeps it
+    c.calculate_target_covariances(O.REG_NONE)
+    c.create_target_voxelmap()
+    vm = O.VoxelMap(pts, np.zeros_like(cov), 1.0, accum_double=True)
+    assert vm.num_buckets > 8192
+    assert c.num_buckets() == vm.num_buckets and c.num_voxels() == vm.num_voxels
+    coords, ids = c.get_voxel_buckets()
+    assert np.array_equal(ids, vm.bucket_id) and np.array_equal(coords, vm.bucket_coord)
+    assert np.array_equal(c.get_voxel_num_points(), vm.vox_n)
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------------------ stage 2b + 3
+def _setup_pair(core, p, method, radius=-1.0, res=1.0):
+    core.set_resolution(res)
+    core.set_neighbor_search_method(method, radius)
+    core.set_target_cloud(p["tgt"])
+    core.find_target_neighbors(20)
+    core.calculate_target_covariances(O.REG_PLANE)
+    core.create_target_voxelmap()
+    core.set_source_cloud(p["src"])
+    core.find_source_neighbors(20)
+    core.calculate_source_covariances(O.REG_PLANE)
+
+
+@pytest.mark.parametrize("method,radius", [(O.DIRECT1, -1), (O.DIRECT7, -1), (O.DIRECT27, -1), (O.DIRECT_RADIUS, 1.5)])
+def test_correspondences_and_linear_system(prepared, relative_pose, method, radius):
+    from fast_gicp_b200.core import Core
+
+    c = Core(0)
+    _setup_pair(c, prepared, method, radius)
+    offs = O.offsets(method, radius)
+    vm = O.VoxelMap(prepared["tgt"], sym(prepared["t_cov"]).astype(np.float32), 1.0, accum_double=True)
+    s_cov = sym(prepared["s_cov"]).astype(np.float32)
+    rng = np.random.default_rng(3)
+    poses = [np.eye(4), relative_pose, relative_pose @ random_pose(rng, 0.02, 0.3)]
+    for T in poses:
+        c.update_correspondences(T)
+        got_pairs = c.get_voxel_correspondences()
+        want_pairs = O.find_correspondences(vm, prepared["src"], T, offs)
+        assert np.array_equal(got_pairs, want_pairs)  # same order (offset-major), same ids
+        for Te in (T, T @ random_pose(rng, 0.005, 0.05)):
+            err, H, b = c.compute_error(Te, True)
+            e0, H0, b0, nc = O.evaluate(vm, prepared["src"], s_cov, offs, T, Te, True)
+            assert nc == len(want_pairs)
+            assert abs(err - e0) <= 2e-5 * abs(e0)
+            assert np.abs(H - H0).max() <= 2e-5 * np.abs(H0).max()
+            assert np.abs(b - b0).max() <= 2e-5 * max(np.abs(b0).max(), 1e-3 * np.abs(H0).max())
+            assert np.array_equal(H, H.T)
+            e1, _, _ = c.compute_error(Te, False)
+            assert abs(e1 - e0) <= 2e-5 * abs(e0)
+            # bitwise reproducible (fixed-order reduction)
+            err2, H2, b2 = c.compute_error(Te, True)
+            assert err2 == err and np.array_equal(H2, H) and np.array_equal(b2, b)
+    c.close()
+
+
+@pytest.mark.parametrize("method", [O.DIRECT1, O.DIRECT7, O.DIRECT27])
+def test_align_matches_oracle_and_ground_truth(prepared, relative_pose, method):
+    """Whole registration vs the float oracle (north_star tolerance) and vs data/relative.txt (reference's gate)."""
+    from fast_gicp_b200.core import Core
+
+    c = Core(0)
+    _setup_pair(c, prepared, method)
+    res = c.align()
+    from fast_gicp_b200.core import pose_from_c
+
+    T = pose_from_c(res.T)
+    vm = O.VoxelMap(prepared["tgt"], sym(prepared["t_cov"]).astype(np.float32), 1.0, accum_double=True)
+    ref = O.align_f32(vm, prepared["src"], sym(prepared["s_cov"]).astype(np.float32), O.offsets(method))
+    assert res.converged and ref.converged
+    assert res.nr_iterations == ref.iterations
+    assert (res.n_linearize, res.n_compute_error) == (ref.n_linearize, ref.n_error)
+    dt, dr = pose_error(ref.T, T)
+    assert dt < TRANS_TOL and dr < ROT_TOL, (dt, dr)
+    Hg = np.array(res.H).reshape(6, 6).T
+    assert np.abs(Hg - ref.H).max() <= 1e-4 * np.abs(ref.H).max()
+    gt_t, gt_r = pose_error(relative_pose, T)
+    assert gt_t < 0.05 and gt_r < np.radians(1.0)
+    c.close()
+
+
+def test_align_17k_pair(pair01, relative_pose):
+    """BASELINE config 2 inputs (17k-pt pair, DIRECT27, res 1.0) end to end against the oracle."""
+    from fast_gicp_b200.core import Core, pose_from_c
+
+    tgt, src = pair01
+    c = Core(0)
+    _setup_pair(c, dict(tgt=tgt, src=src), O.DIRECT27)
+    res = c.align()
+    ref = O.register_f32(tgt, src, method=O.DIRECT27, accum_double=True)
+    dt, dr = pose_error(ref.T, pose_from_c(res.T))
+    assert res.converged and dt < TRANS_TOL and dr < ROT_TOL, (dt, dr)
+    gt_t, gt_r = pose_error(relative_pose, pose_from_c(res.T))
+    assert gt_t < 0.05 and gt_r < np.radians(1.0)
+    c.close()
+
+
+# ------------------------------------------------------------------------------------- reference test scenarios (API)
+def test_reference_alignment_scenarios(pair02, relative_pose):
+    """src/test/gicp_test.cpp:147-201 re-expressed on the FastVGICPCuda mirror: forward, backward, swap+setSource, swap+setTarget."""
+    from fast_gicp_b200 import FastVGICPCuda
+
+    target, source = pair02
+    t_tol, r_tol = 0.05, np.radians(1.0)
+
+    reg = FastVGICPCuda()
+    reg.setInputTarget(target)
+    reg.setInputSource(source)
+    T = reg.align()
+    e = pose_error(relative_pose, T)
+    assert e[0] < t_tol and e[1] < r_tol and reg.hasConverged(), "FORWARD TEST"
+
+    reg.setInputTarget(source)
+    reg.setInputSource(target)
+    T = reg.align()
+    e = pose_error(relative_pose, np.linalg.inv(T.astype(np.float64)))
+    assert e[0] < t_tol and e[1] < r_tol and reg.hasConverged(), "BACKWARD TEST"
+
+    reg = FastVGICPCuda()
+    reg.setInputSource(target)
+    reg.swapSourceAndTarget()
+    reg.setInputSource(source)
+    T = reg.align()
+    e = pose_error(relative_pose, T)
+    assert e[0] < t_tol and e[1] < r_tol and reg.hasConverged(), "SWAP AND SET SOURCE TEST"
+
+    reg = FastVGICPCuda()
+    reg.setInputTarget(source)
+    reg.swapSourceAndTarget()
+    reg.setInputTarget(target)
+    T = reg.align()
+    e = pose_error(relative_pose, T)
+    assert e[0] < t_tol and e[1] < r_tol and reg.hasConverged(), "SWAP AND SET TARGET TEST"
+
+
+# ------------------------------------------------------------------------------------------------------- edge cases
+def test_error_states_and_edge_cases():
+    from fast_gicp_b200.core import Core, VgicpError, ERR_BAD_STATE, ERR_INVALID_ARGUMENT
+
+    c = Core(0)
+    with pytest.raises(VgicpError) as e:
+        c.find_source_neighbors(20)
+    assert e.value.code == ERR_BAD_STATE
+    with pytest.raises(VgicpError) as e:
+        c.create_target_voxelmap()
+    assert e.value.code == ERR_BAD_STATE
+    with pytest.raises(VgicpError) as e:
+        c.compute_error(np.eye(4))
+    assert e.value.code == ERR_BAD_STATE
+    pts = np.random.default_rng(0).uniform(-5, 5, (10, 3)).astype(np.float32)
+    c.set_source_cloud(pts)
+    with pytest.raises(VgicpError) as e:
+        c.find_source_neighbors(20)  # k > n
+    assert e.value.code == ERR_INVALID_ARGUMENT
+    with pytest.raises(VgicpError) as e:
+        c.set_source_neighbors(3, np.zeros(7, dtype=np.int32))  # k*n mismatch (the reference asserts)
+    assert e.value.code == ERR_INVALID_ARGUMENT
+    with pytest.raises(VgicpError) as e:
+        c.set_neighbor_search_method(17)  # the reference abort()s
+    assert e.value.code == ERR_INVALID_ARGUMENT
+    c.set_target_cloud(np.zeros((0, 3), dtype=np.float32))  # empty cloud accepted, map refused
+    assert c.num_target_points() == 0
+    # strided input (pcl::PointXYZI = 32 bytes/pt)
+    rec = np.zeros((10, 8), dtype=np.float32)
+    rec[:, :3] = pts
+    c.set_source_cloud(rec)
+    c.find_source_neighbors(5)
+    assert np.array_equal(c.get_source_neighbors(), O.knn(pts, 5, "bruteforce"))
+    c.close()
+
+
+def test_source_outside_map_gives_zero_system(prepared):
+    """No correspondences (source far away from every voxel): H = 0, b = 0, err = 0."""
+    from fast_gicp_b200.core import Core
+
+    c = Core(0)
+    _setup_pair(c, prepared, O.DIRECT7)
+    T = np.eye(4)
+    T[:3, 3] = [1000.0, 1000.0, 1000.0]
+    err, H, b = c.linearize(T)
+    assert err == 0.0 and not H.any() and not b.any()
+    assert len(c.get_voxel_correspondences()) == 0
+    c.close()
