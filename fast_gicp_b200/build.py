@@ -27,8 +27,8 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def _sources():
-    return [os.path.join(CSRC, "vgicp_b200.cu")]
+# (source, extra nvcc flags).  vgicp_stage1.cu must not contract a*b+c: its results are compared bit-for-bit.
+UNITS = [("vgicp_b200.cu", []), ("vgicp_stage1.cu", ["--fmad=false"])]
 
 
 def _deps():
@@ -51,9 +51,16 @@ def build_native(force=False, verbose=False):
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}  # the image's CC wrapper lacks libgomp specs
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
-                                                                                "-shared", "-o", LIB_PATH] + _sources()
-    subprocess.check_call(cmd, env=env)
+    ccbin = ["-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    objs = []
+    for src, extra in UNITS:
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ccbin + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        subprocess.check_call(cmd, env=env)
+        objs.append(obj)
+    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + ccbin + objs, env=env)
     return LIB_PATH
 
 

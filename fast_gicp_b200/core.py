@@ -197,7 +197,7 @@ class Core:
         a = np.asarray(points)
         if a.dtype != np.float32 or a.ndim != 2 or a.shape[1] < 3 or not a.flags.c_contiguous:
             a = np.ascontiguousarray(np.asarray(points, dtype=np.float32)[:, :3])
-        return a, a.shape[0], a.strides[0]
+        return a, a.shape[0], a.shape[1] * 4  # (strides of an empty array are not meaningful)
 
     def set_source_cloud(self, points):
         a, n, stride = self._cloud(points)

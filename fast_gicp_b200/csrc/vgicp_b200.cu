@@ -175,15 +175,8 @@ int find_neighbors(vgicp_handle h, Cloud& c, int k) {
   if (!c.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "find_neighbors: cloud not set");
   if (k <= 0 || k > kMaxK || k > c.n) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "find_neighbors: need 1 <= k <= min(num_points, 64)");
   CU_TRY(h, c.nbr.reserve((size_t)c.n * k));
-  size_t smem = sizeof(float4) * kKnnTile + (size_t)k * kKnnThreads * (sizeof(float) + sizeof(int));
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU_TRY(h, cudaFuncSetAttribute(k_knn_bruteforce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float4) * kKnnTile + (size_t)kMaxK * kKnnThreads * 8)));
-    attr_set = true;
-  }
-  k_knn_bruteforce<<<blocks_for(c.n, kKnnThreads), kKnnThreads, smem, h->stream>>>(c.pts.p, c.n, k, c.nbr.p);
+  CU_TRY(h, launch_knn_bruteforce(c.pts.p, c.n, k, c.nbr.p, h->stream));
   h->launches++;
-  CU_TRY(h, cudaGetLastError());
   c.k = k;
   return VGICP_OK;
 }
@@ -194,9 +187,8 @@ int calc_covariances(vgicp_handle h, Cloud& c, int method) {
   CU_TRY(h, c.covA.reserve(c.n));
   CU_TRY(h, c.covB.reserve(c.n));
   if (c.n > 0) {
-    k_covariance_knn<<<blocks_for(c.n, 128), 128, 0, h->stream>>>(c.pts.p, c.nbr.p, c.n, c.k, method, c.covA.p, c.covB.p);
+    CU_TRY(h, launch_covariance_knn(c.pts.p, c.nbr.p, c.n, c.k, method, c.covA.p, c.covB.p, h->stream));
     h->launches++;
-    CU_TRY(h, cudaGetLastError());
   }
   c.has_cov = true;
   if (method == VGICP_REG_NORMALIZED_MIN_EIG)
@@ -210,9 +202,8 @@ int calc_covariances_rbf(vgicp_handle h, Cloud& c, int method) {
   CU_TRY(h, c.covA.reserve(c.n));
   CU_TRY(h, c.covB.reserve(c.n));
   if (c.n > 0) {
-    k_covariance_rbf<<<blocks_for(c.n, 128), 128, 0, h->stream>>>(c.pts.p, c.n, (float)h->kernel_width, (float)h->kernel_max_dist, method, c.covA.p, c.covB.p);
+    CU_TRY(h, launch_covariance_rbf(c.pts.p, c.n, (float)h->kernel_width, (float)h->kernel_max_dist, method, c.covA.p, c.covB.p, h->stream));
     h->launches++;
-    CU_TRY(h, cudaGetLastError());
   }
   c.has_cov = true;
   if (method == VGICP_REG_NORMALIZED_MIN_EIG) return fail(h, VGICP_ERR_UNSUPPORTED, "unimplemented covariance regularization method was selected; raw covariances kept");

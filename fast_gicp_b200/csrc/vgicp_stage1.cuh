@@ -1,0 +1,20 @@
+// vgicp_stage1.cuh -- launchers of the stage 1 kernels (vgicp_stage1.cu, compiled with --fmad=false).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace vgicp {
+
+constexpr int kMaxK = 64;         // k-NN list capacity
+constexpr int kKnnThreads = 128;  // queries per block in the brute-force k-NN
+constexpr int kKnnTile = 512;     // targets staged in shared memory per step
+constexpr int kRbfBlock = 512;    // covariance_estimation_rbf.cu:60 BLOCK_SIZE
+
+// exact k-NN of every point inside its own cloud; rows ascending in (d2, index)
+cudaError_t launch_knn_bruteforce(const float4* pts, int n, int k, int* nbr, cudaStream_t stream);
+// covariance_estimation + covariance_regularization(method) fused; symmetric-packed output
+cudaError_t launch_covariance_knn(const float4* pts, const int* nbr, int n, int k, int method, float4* covA, float2* covB, cudaStream_t stream);
+// covariance_estimation_rbf + covariance_regularization(method)
+cudaError_t launch_covariance_rbf(const float4* pts, int n, float exp_factor, float max_dist, int method, float4* covA, float2* covB, cudaStream_t stream);
+
+}  // namespace vgicp

@@ -310,9 +310,12 @@ static void eig3_roots(const float* m, float* roots) {
   float q = a_over_3 * a_over_3 * a_over_3 - half_b * half_b;
   if (q < 0.0f) q = 0.0f;
   float rho = sqrtf(a_over_3);
-  float theta = atan2f(sqrtf(q), half_b) * s_inv3;
-  float cos_theta = cosf(theta);
-  float sin_theta = sinf(theta);
+  /* atan2/cos/sin evaluated in double and rounded once to float: the correctly rounded float results, independent of
+   * the libm underneath (Eigen calls the float functions of whatever platform it runs on: CUDA's are 2-ulp). The CUDA
+   * path does the same, which makes the regularised covariances comparable bit-for-bit. */
+  float theta = (float)atan2((double)sqrtf(q), (double)half_b) * s_inv3;
+  float cos_theta = (float)cos((double)theta);
+  float sin_theta = (float)sin((double)theta);
   roots[0] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
   roots[1] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
   roots[2] = c2_over_3 + 2.0f * rho * cos_theta;

@@ -72,20 +72,20 @@ def test_raw_covariance_bit_exact(core, prepared):
     assert np.array_equal(got, prepared["t_raw"])
 
 
-@pytest.mark.parametrize("method,tol", [(O.REG_PLANE, 3e-5), (O.REG_MIN_EIG, 3e-5), (O.REG_FROBENIUS, 3e-5)])
-def test_regularised_covariance(core, prepared, method, tol):
-    """Same closed-form eigen-solver on both sides; libm vs CUDA atan2f/cosf/sinf differ by ulps, and the GPU keeps the
-    symmetric part of V L V^-1."""
+@pytest.mark.parametrize("method", [O.REG_PLANE, O.REG_MIN_EIG, O.REG_FROBENIUS])
+def test_regularised_covariance_bit_exact(core, prepared, method):
+    """covariance_regularization.cu restated with the same operation order on both sides (stage 1 is compiled with
+    --fmad=false, trig evaluated in double and rounded once): the regularised covariances agree bit-for-bit, including on
+    line-like neighbourhoods where the closed-form eigen-solver amplifies 1-ulp differences to percent level.  The GPU
+    stores the symmetric part of V L V^-1."""
     core.set_target_cloud(prepared["tgt"])
     core.set_target_neighbors(20, prepared["t_nbr"])
     core.calculate_target_covariances(method)
     got = core.get_target_covariances()
-    want = sym(O.regularize(prepared["t_raw"], method))
-    scale = np.maximum(1.0, np.abs(want).max(axis=1, keepdims=True))
-    err = np.abs(got - want) / scale
-    # ill-conditioned neighbourhoods amplify ulp differences: allow a handful of outliers, none large
-    assert np.percentile(err, 99.9) < tol, np.percentile(err, 99.9)
-    assert err.max() < 5e-3, err.max()
+    want = sym(O.regularize(prepared["t_raw"], method)).astype(np.float32)
+    bad = np.flatnonzero((got != want).any(axis=1))
+    # a double-rounding coincidence in the double->float trig step is conceivable (p ~ 1e-8 per point); allow one
+    assert len(bad) <= 1, (len(bad), np.abs(got - want).max())
 
 
 def test_plane_regularisation_identity(core, prepared):
@@ -134,9 +134,10 @@ def test_voxelmap_table_bit_exact(prepared, res):
     assert disp.max() < 10
     assert np.array_equal(c.get_voxel_num_points(), vm.vox_n)
     # means / covs: GPU accumulates in double and rounds once == oracle accum_double mode (GPU covariances differ by ulps)
+    # (double atomics: the order of additions is free, the rounded float result is not, up to a last-bit tie)
     assert np.abs(c.get_voxel_means() - vm.vox_mean).max() < 1e-5
-    cov_err = np.abs(c.get_voxel_covs() - vm.vox_cov).max(axis=1)  # single-point voxels inherit the per-point outliers
-    assert np.percentile(cov_err, 99.5) < 5e-5 and cov_err.max() < 5e-3, (np.percentile(cov_err, 99.5), cov_err.max())
+    assert np.abs(c.get_voxel_covs() - vm.vox_cov).max() < 1e-6
+    assert (c.get_voxel_means() == vm.vox_mean).mean() > 0.999 and (c.get_voxel_covs() == vm.vox_cov).mean() > 0.999
     # the reference's float accumulation (any order) stays within float rounding of it
     vmf = O.VoxelMap(prepared["tgt"], sym(prepared["t_cov"]).astype(np.float32), res, accum_double=False)
     assert np.abs(c.get_voxel_means() - vmf.vox_mean).max() < 2e-4
