@@ -1,14 +1,17 @@
 """Build the native library in-tree: fast_gicp_b200/lib/libvgicp_b200.so (sm_100a only, -lineinfo).
 
-    python -m fast_gicp_b200.build [--force]
+    python build_native.py [--force] [-v]
+
+Lives outside the package on purpose: importing fast_gicp_b200 requires the built library (no CPU fallback), so the
+builder must be importable without it.
 """
 import os
 import shutil
 import subprocess
 import sys
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
+ROOT = os.path.dirname(os.path.abspath(__file__))
+HERE = os.path.join(ROOT, "fast_gicp_b200")
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libvgicp_b200.so")

@@ -34,7 +34,9 @@ EXPORTED_SYMBOLS = [
     "vgicp_update_correspondences", "vgicp_get_voxel_correspondences", "vgicp_compute_error",
     "vgicp_lsq_default_params", "vgicp_align", "vgicp_transform_source",
     "vgicp_get_launch_count", "vgicp_synchronize", "vgicp_get_stream",
+    "vgicp_set_source_cloud_device", "vgicp_set_target_cloud_device", "vgicp_set_profiling", "vgicp_get_profile", "vgicp_profile_category_name",
 ]
+PROF_NUM_CATEGORIES = 7
 
 
 class VgicpError(RuntimeError):
@@ -75,7 +77,7 @@ def load_library():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: run `python -m fast_gicp_b200.build` (the CUDA library is required; there is no CPU fallback)")
+        raise ImportError(f"{LIB_PATH} is missing: run `python build_native.py` (the CUDA library is required; there is no CPU fallback)")
     L = C.CDLL(LIB_PATH)
     hp, fp, ip, dp = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)
     sig = {
@@ -117,6 +119,10 @@ def load_library():
         "vgicp_get_launch_count": [hp, C.POINTER(C.c_uint64)],
         "vgicp_synchronize": [hp],
         "vgicp_get_stream": [hp, C.POINTER(C.c_uint64)],
+        "vgicp_set_source_cloud_device": [hp, C.c_void_p, C.c_size_t, C.c_size_t],
+        "vgicp_set_target_cloud_device": [hp, C.c_void_p, C.c_size_t, C.c_size_t],
+        "vgicp_set_profiling": [hp, C.c_int],
+        "vgicp_get_profile": [hp, dp, C.POINTER(C.c_uint64), C.c_int],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -125,6 +131,8 @@ def load_library():
     L.vgicp_lsq_default_params.restype = None
     L.vgicp_last_error.argtypes = [hp]
     L.vgicp_last_error.restype = C.c_char_p
+    L.vgicp_profile_category_name.argtypes = [C.c_int]
+    L.vgicp_profile_category_name.restype = C.c_char_p
     L.vgicp_version.argtypes = []
     L.vgicp_version.restype = C.c_char_p
     _lib = L
@@ -211,6 +219,21 @@ class Core:
         """Host pointer + size straight through (used by bench.py with pinned buffers)."""
         fn = self._lib.vgicp_set_source_cloud if which == "source" else self._lib.vgicp_set_target_cloud
         self._check(fn(self._h, ptr, n, stride))
+
+    def set_cloud_device(self, which, dev_ptr, n, stride):
+        """Points already resident in this GPU's memory (e.g. a torch CUDA tensor's data_ptr())."""
+        fn = self._lib.vgicp_set_source_cloud_device if which == "source" else self._lib.vgicp_set_target_cloud_device
+        self._check(fn(self._h, dev_ptr, n, stride))
+
+    def set_profiling(self, enable):
+        self._check(self._lib.vgicp_set_profiling(self._h, int(bool(enable))))
+
+    def get_profile(self):
+        """-> {category: (total_ms, launches)} since profiling was enabled."""
+        ms = (C.c_double * PROF_NUM_CATEGORIES)()
+        cnt = (C.c_uint64 * PROF_NUM_CATEGORIES)()
+        self._check(self._lib.vgicp_get_profile(self._h, ms, cnt, PROF_NUM_CATEGORIES))
+        return {self._lib.vgicp_profile_category_name(i).decode(): (ms[i], cnt[i]) for i in range(PROF_NUM_CATEGORIES)}
 
     def swap_source_and_target(self):
         self._check(self._lib.vgicp_swap_source_and_target(self._h))
@@ -356,9 +379,13 @@ class Core:
         self._check(self._lib.vgicp_align(self._h, _dp(g), C.byref(params), C.byref(res)))
         return res
 
-    def transform_source(self, T, stride=12):
+    def transform_source(self, T, stride=12, out=None):
         n = self.num_source_points()
-        out = np.zeros((n, stride // 4), dtype=np.float32)
+        if out is None:
+            out = np.zeros((n, stride // 4), dtype=np.float32)
+        else:
+            assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape[0] >= n
+            stride = out.shape[1] * 4
         t = pose_to_c(T)
         self._check(self._lib.vgicp_transform_source(self._h, _dp(t), out.ctypes.data, n, stride))
         return out

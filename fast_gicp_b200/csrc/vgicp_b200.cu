@@ -102,6 +102,14 @@ struct vgicp_context {
   double* d_out = nullptr;    // 43 doubles
   double* h_out = nullptr;    // pinned
   int* h_counters = nullptr;  // pinned
+
+  // optional per-kernel timing (vgicp_set_profiling): CUDA events on the handle's stream around every launch
+  bool prof_on = false;
+  struct ProfRec { int cat; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[VGICP_PROF_NUM_CATEGORIES] = {0};
+  uint64_t prof_launches[VGICP_PROF_NUM_CATEGORIES] = {0};
 };
 
 namespace {
@@ -110,6 +118,36 @@ int fail(vgicp_handle h, int code, const std::string& msg) {
   if (h) h->err = msg;
   return code;
 }
+
+cudaEvent_t prof_event(vgicp_handle h) {
+  if (!h->prof_pool.empty()) {
+    cudaEvent_t e = h->prof_pool.back();
+    h->prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+inline void prof_begin(vgicp_handle h, int cat) {
+  h->prof_launches[cat]++;
+  if (!h->prof_on) return;
+  vgicp_context::ProfRec r{cat, prof_event(h), prof_event(h)};
+  cudaEventRecord(r.a, h->stream);
+  h->prof_pending.push_back(r);
+}
+inline void prof_end(vgicp_handle h) {
+  if (!h->prof_on) return;
+  cudaEventRecord(h->prof_pending.back().b, h->stream);
+}
+// every kernel launch of the library goes through here: counts it, optionally brackets it with events
+#define KLAUNCH(h, cat, ...) \
+  do {                       \
+    prof_begin(h, cat);      \
+    __VA_ARGS__;             \
+    prof_end(h);             \
+    (h)->launches++;         \
+  } while (0)
 
 #define CU_TRY(h, expr)                                                                                       \
   do {                                                                                                        \
@@ -143,7 +181,7 @@ Pose to_pose(const double* T) {  // Eigen::Isometry3d (column-major) -> float im
   return p;
 }
 
-int set_cloud(vgicp_handle h, Cloud& c, const float* xyz, size_t n, size_t stride) {
+int set_cloud(vgicp_handle h, Cloud& c, const float* xyz, size_t n, size_t stride, bool on_device = false) {
   if (n > 0 && !xyz) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_cloud: null points");
   if (stride < 12 || (stride % 4) != 0) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_cloud: stride_bytes must be a multiple of 4 and >= 12");
   if (n > (size_t)0x7fffffff / 64) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_cloud: too many points");
@@ -151,10 +189,14 @@ int set_cloud(vgicp_handle h, Cloud& c, const float* xyz, size_t n, size_t strid
   c.n = (int)n;
   c.has_pts = true;
   if (n == 0) return VGICP_OK;
+  if (on_device) {  // caller's buffer already lives in this GPU's memory: read it in place (stream-ordered)
+    KLAUNCH(h, VGICP_PROF_UNPACK, k_unpack_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(reinterpret_cast<const unsigned char*>(xyz), stride, (int)n, c.pts.p));
+    CU_TRY(h, cudaGetLastError());
+    return VGICP_OK;
+  }
   CU_TRY(h, h->staging.reserve(n * stride));
   CU_TRY(h, cudaMemcpyAsync(h->staging.p, xyz, n * stride, cudaMemcpyHostToDevice, h->stream));
-  k_unpack_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->staging.p, stride, (int)n, c.pts.p);
-  h->launches++;
+  KLAUNCH(h, VGICP_PROF_UNPACK, k_unpack_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->staging.p, stride, (int)n, c.pts.p));
   CU_TRY(h, cudaGetLastError());
   // the caller may free/modify xyz after return: pageable copies are staged synchronously by the driver, pinned ones are not
   CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -175,8 +217,9 @@ int find_neighbors(vgicp_handle h, Cloud& c, int k) {
   if (!c.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "find_neighbors: cloud not set");
   if (k <= 0 || k > kMaxK || k > c.n) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "find_neighbors: need 1 <= k <= min(num_points, 64)");
   CU_TRY(h, c.nbr.reserve((size_t)c.n * k));
-  CU_TRY(h, launch_knn_bruteforce(c.pts.p, c.n, k, c.nbr.p, h->stream));
-  h->launches++;
+  cudaError_t ke = cudaSuccess;
+  KLAUNCH(h, VGICP_PROF_KNN, ke = launch_knn_bruteforce(c.pts.p, c.n, k, c.nbr.p, h->stream));
+  CU_TRY(h, ke);
   c.k = k;
   return VGICP_OK;
 }
@@ -187,8 +230,9 @@ int calc_covariances(vgicp_handle h, Cloud& c, int method) {
   CU_TRY(h, c.covA.reserve(c.n));
   CU_TRY(h, c.covB.reserve(c.n));
   if (c.n > 0) {
-    CU_TRY(h, launch_covariance_knn(c.pts.p, c.nbr.p, c.n, c.k, method, c.covA.p, c.covB.p, h->stream));
-    h->launches++;
+    cudaError_t ke = cudaSuccess;
+    KLAUNCH(h, VGICP_PROF_COVARIANCE, ke = launch_covariance_knn(c.pts.p, c.nbr.p, c.n, c.k, method, c.covA.p, c.covB.p, h->stream));
+    CU_TRY(h, ke);
   }
   c.has_cov = true;
   if (method == VGICP_REG_NORMALIZED_MIN_EIG)
@@ -202,8 +246,9 @@ int calc_covariances_rbf(vgicp_handle h, Cloud& c, int method) {
   CU_TRY(h, c.covA.reserve(c.n));
   CU_TRY(h, c.covB.reserve(c.n));
   if (c.n > 0) {
-    CU_TRY(h, launch_covariance_rbf(c.pts.p, c.n, (float)h->kernel_width, (float)h->kernel_max_dist, method, c.covA.p, c.covB.p, h->stream));
-    h->launches++;
+    cudaError_t ke = cudaSuccess;
+    KLAUNCH(h, VGICP_PROF_COVARIANCE, ke = launch_covariance_rbf(c.pts.p, c.n, (float)h->kernel_width, (float)h->kernel_max_dist, method, c.covA.p, c.covB.p, h->stream));
+    CU_TRY(h, ke);
   }
   c.has_cov = true;
   if (method == VGICP_REG_NORMALIZED_MIN_EIG) return fail(h, VGICP_ERR_UNSUPPORTED, "unimplemented covariance regularization method was selected; raw covariances kept");
@@ -255,17 +300,16 @@ int build_voxelmap(vgicp_handle h) {
   const int n = t.n;
   CU_TRY(h, m.coords.reserve(n));
   CU_TRY(h, m.slot_of_point.reserve(n));
-  k_voxel_coords<<<blocks_for(n, 256), 256, 0, h->stream>>>(t.pts.p, n, m.res, m.coords.p);
-  h->launches++;
+  KLAUNCH(h, VGICP_PROF_VOXELMAP, k_voxel_coords<<<blocks_for(n, 256), 256, 0, h->stream>>>(t.pts.p, n, m.res, m.coords.p));
   int B = m.init_num_buckets;
   for (;; B *= 2) {  // :265 (no upper bound in the reference; bounded here)
     if (B > (1 << 28)) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "create_target_voxelmap: hash table would exceed 2^28 buckets");
     CU_TRY(h, m.slots.reserve(B));
-    k_fill_i32<<<blocks_for(B, 256), 256, 0, h->stream>>>(m.slots.p, -1, (size_t)B);
+    KLAUNCH(h, VGICP_PROF_VOXELMAP, k_fill_i32<<<blocks_for(B, 256), 256, 0, h->stream>>>(m.slots.p, -1, (size_t)B));
     CU_TRY(h, cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(int), h->stream));
-    k_table_insert<<<blocks_for(n, 256), 256, 0, h->stream>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan);
-    k_table_lookup_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan, m.slot_of_point.p, h->d_counters);
-    h->launches += 3;
+    KLAUNCH(h, VGICP_PROF_VOXELMAP, k_table_insert<<<blocks_for(n, 256), 256, 0, h->stream>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan));
+    KLAUNCH(h, VGICP_PROF_VOXELMAP,
+            k_table_lookup_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan, m.slot_of_point.p, h->d_counters));
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -273,8 +317,7 @@ int build_voxelmap(vgicp_handle h) {
   }
   m.num_buckets = B;
   CU_TRY(h, m.buckets.reserve(B));
-  k_table_assign_ids<<<1, 1024, 0, h->stream>>>(m.coords.p, m.slots.p, B, m.buckets.p, h->d_counters + 1);
-  h->launches++;
+  KLAUNCH(h, VGICP_PROF_VOXELMAP, k_table_assign_ids<<<1, 1024, 0, h->stream>>>(m.coords.p, m.slots.p, B, m.buckets.p, h->d_counters + 1));
   CU_TRY(h, cudaMemcpyAsync(h->h_counters + 1, h->d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   const int V = h->h_counters[1];
@@ -285,9 +328,9 @@ int build_voxelmap(vgicp_handle h) {
   if (V > 0) {
     CU_TRY(h, cudaMemsetAsync(m.sums.p, 0, sizeof(double) * 10 * (size_t)V, h->stream));
     CU_TRY(h, cudaMemsetAsync(m.counts.p, 0, sizeof(int) * (size_t)V, h->stream));
-    k_voxel_accumulate<<<blocks_for(n, 256), 256, 0, h->stream>>>(t.pts.p, t.covA.p, t.covB.p, n, m.slot_of_point.p, m.buckets.p, m.sums.p, m.counts.p);
-    k_voxel_finalize<<<blocks_for(V, 256), 256, 0, h->stream>>>(m.sums.p, m.counts.p, V, m.vox.p);
-    h->launches += 2;
+    KLAUNCH(h, VGICP_PROF_VOXELMAP,
+            k_voxel_accumulate<<<blocks_for(n, 256), 256, 0, h->stream>>>(t.pts.p, t.covA.p, t.covB.p, n, m.slot_of_point.p, m.buckets.p, m.sums.p, m.counts.p));
+    KLAUNCH(h, VGICP_PROF_VOXELMAP, k_voxel_finalize<<<blocks_for(V, 256), 256, 0, h->stream>>>(m.sums.p, m.counts.p, V, m.vox.p));
     CU_TRY(h, cudaGetLastError());
   }
   m.built = true;
@@ -311,6 +354,7 @@ int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H) {
     if (want_H) k_linearize<MODE, true><<<grid, kLinThreads, 0, h->stream>>>(a);    \
     else k_linearize<MODE, false><<<grid, kLinThreads, 0, h->stream>>>(a);          \
   } while (0)
+  prof_begin(h, want_H ? VGICP_PROF_LINEARIZE : VGICP_PROF_ERROR);
   switch (h->offset_mode) {
     case 1: LAUNCH_LIN(1); break;
     case 7: LAUNCH_LIN(7); break;
@@ -318,6 +362,7 @@ int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H) {
     default: LAUNCH_LIN(0); break;
   }
 #undef LAUNCH_LIN
+  prof_end(h);
   h->launches++;
   CU_TRY(h, cudaGetLastError());
   return VGICP_OK;
@@ -403,6 +448,8 @@ int vgicp_destroy(vgicp_handle h) {
   if (h->d_out) cudaFree(h->d_out);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_counters) cudaFreeHost(h->h_counters);
+  for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : h->prof_pool) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return VGICP_OK;
@@ -672,9 +719,9 @@ int vgicp_get_voxel_correspondences(vgicp_handle h, int* pairs, size_t cap, size
   std::vector<int> ids(total);
   if (total) {
     CU_TRY(h, h->corr_ids.reserve(total));
-    k_correspondence_ids<<<blocks_for(n, 128), 128, 0, h->stream>>>(h->source.pts.p, n, h->map.buckets.p, (unsigned)(h->map.num_buckets - 1), h->map.max_scan, h->d_offsets.p, n_off,
-                                                                     h->map.res, h->lin, h->corr_ids.p);
-    h->launches++;
+    KLAUNCH(h, VGICP_PROF_OTHER,
+            k_correspondence_ids<<<blocks_for(n, 128), 128, 0, h->stream>>>(h->source.pts.p, n, h->map.buckets.p, (unsigned)(h->map.num_buckets - 1), h->map.max_scan, h->d_offsets.p,
+                                                                             n_off, h->map.res, h->lin, h->corr_ids.p));
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaMemcpyAsync(ids.data(), h->corr_ids.p, total * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -798,13 +845,61 @@ int vgicp_transform_source(vgicp_handle h, const double T[16], float* out_xyz, s
   if (n == 0) return VGICP_OK;
   CU_TRY(h, h->staging.reserve((size_t)n * stride));
   // keep the non-xyz bytes of the caller's records untouched: copy in, overwrite xyz, copy out
-  CU_TRY(h, cudaMemcpyAsync(h->staging.p, out_xyz, (size_t)n * stride, cudaMemcpyHostToDevice, h->stream));
-  k_transform_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->source.pts.p, n, to_pose(T), h->staging.p, stride);
-  h->launches++;
+  if (stride > 12) CU_TRY(h, cudaMemcpyAsync(h->staging.p, out_xyz, (size_t)n * stride, cudaMemcpyHostToDevice, h->stream));
+  KLAUNCH(h, VGICP_PROF_OTHER, k_transform_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->source.pts.p, n, to_pose(T), h->staging.p, stride));
   CU_TRY(h, cudaGetLastError());
   CU_TRY(h, cudaMemcpyAsync(out_xyz, h->staging.p, (size_t)n * stride, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   return VGICP_OK;
+}
+
+int vgicp_set_source_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, size_t stride_bytes) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  h->source.k = 0;
+  h->source.has_cov = false;
+  return set_cloud(h, h->source, d_xyz, n, stride_bytes, true);
+}
+
+int vgicp_set_target_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, size_t stride_bytes) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  h->target.k = 0;
+  h->target.has_cov = false;
+  h->map.built = false;
+  return set_cloud(h, h->target, d_xyz, n, stride_bytes, true);
+}
+
+int vgicp_set_profiling(vgicp_handle h, int enable) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  for (auto& r : h->prof_pending) { h->prof_pool.push_back(r.a); h->prof_pool.push_back(r.b); }
+  h->prof_pending.clear();
+  for (int i = 0; i < VGICP_PROF_NUM_CATEGORIES; i++) { h->prof_ms[i] = 0.0; h->prof_launches[i] = 0; }
+  h->prof_on = enable != 0;
+  return VGICP_OK;
+}
+
+int vgicp_get_profile(vgicp_handle h, double* ms, uint64_t* launches, int capacity) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (!ms || !launches || capacity < VGICP_PROF_NUM_CATEGORIES) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_profile: need VGICP_PROF_NUM_CATEGORIES entries");
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  for (auto& r : h->prof_pending) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) h->prof_ms[r.cat] += (double)t;
+    h->prof_pool.push_back(r.a);
+    h->prof_pool.push_back(r.b);
+  }
+  h->prof_pending.clear();
+  for (int i = 0; i < VGICP_PROF_NUM_CATEGORIES; i++) { ms[i] = h->prof_ms[i]; launches[i] = h->prof_launches[i]; }
+  return VGICP_OK;
+}
+
+const char* vgicp_profile_category_name(int category) {
+  static const char* names[VGICP_PROF_NUM_CATEGORIES] = {"unpack_points", "knn", "covariance", "voxelmap_build", "linearize", "compute_error", "other"};
+  return (category >= 0 && category < VGICP_PROF_NUM_CATEGORIES) ? names[category] : "";
 }
 
 int vgicp_get_launch_count(vgicp_handle h, uint64_t* launches) {

@@ -220,10 +220,12 @@ class FastVGICPCuda(LsqRegistration):
         err, H, b = self.vgicp_cuda_.linearize(np.asarray(relative_pose, dtype=np.float32).astype(np.float64))
         return (err, H, b) if want_H else err
 
-    def align(self, initial_guess=None, return_aligned=False):
+    def align(self, initial_guess=None, return_aligned=False, aligned_out=None):
         """pcl::Registration::align -> computeTransformation (:144-148 + lsq_registration_impl.hpp:53-79).
 
-        Returns the final 4x4 float transformation (pygicp's align); `return_aligned` also returns the transformed source.
+        Returns the final 4x4 float transformation (pygicp's align).  The C++ align(output, guess) also fills `output`
+        with the transformed source (pcl::transformPointCloud, lsq_registration_impl.hpp:78): pass `aligned_out`
+        ((N,3) float32, written in place) or `return_aligned=True` to get it.
         """
         if self.input_ is None or self.target_ is None:
             raise RuntimeError("align: input source/target not set")
@@ -237,6 +239,8 @@ class FastVGICPCuda(LsqRegistration):
         self.converged_ = bool(res.converged)
         self.final_hessian_ = np.array(res.H).reshape(6, 6).T.copy()
         self.final_transformation_ = _core.pose_from_c(res.T).astype(np.float32)
+        if aligned_out is not None:
+            self.vgicp_cuda_.transform_source(self.final_transformation_.astype(np.float64), out=aligned_out)
         if return_aligned:
             return self.final_transformation_, self.vgicp_cuda_.transform_source(self.final_transformation_.astype(np.float64))[:, :3]
         return self.final_transformation_

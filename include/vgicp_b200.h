@@ -148,6 +148,18 @@ VGICP_API void vgicp_lsq_default_params(vgicp_lsq_params* p);
 VGICP_API int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* params, vgicp_align_result* result);
 /* pcl::transformPointCloud of the source by T (lsq_registration_impl.hpp:78) on the device; out: n x stride floats */
 VGICP_API int vgicp_transform_source(vgicp_handle h, const double T[16], float* out_xyz, size_t capacity_points, size_t stride_bytes);
+/* set_{source,target}_cloud with the points already resident in this GPU's memory (device pointer, same layout rules);
+ * the read is stream-ordered on the handle's stream, the caller keeps the buffer alive until the next synchronising call */
+VGICP_API int vgicp_set_source_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, size_t stride_bytes);
+VGICP_API int vgicp_set_target_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, size_t stride_bytes);
+/* per-kernel timing with CUDA events on the handle's stream (off by default; enabling resets the counters) */
+enum {
+  VGICP_PROF_UNPACK = 0, VGICP_PROF_KNN = 1, VGICP_PROF_COVARIANCE = 2, VGICP_PROF_VOXELMAP = 3, VGICP_PROF_LINEARIZE = 4, VGICP_PROF_ERROR = 5,
+  VGICP_PROF_OTHER = 6, VGICP_PROF_NUM_CATEGORIES = 7
+};
+VGICP_API int vgicp_set_profiling(vgicp_handle h, int enable);
+VGICP_API int vgicp_get_profile(vgicp_handle h, double* ms_per_category, uint64_t* launches_per_category, int capacity);
+VGICP_API const char* vgicp_profile_category_name(int category);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 VGICP_API int vgicp_get_launch_count(vgicp_handle h, uint64_t* launches);
 VGICP_API int vgicp_synchronize(vgicp_handle h);

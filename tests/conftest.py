@@ -21,7 +21,7 @@ def _build_everything():
     import oracle
 
     oracle.build()
-    from fast_gicp_b200 import build as b
+    import build_native as b
 
     b.build_native()
 
