@@ -95,6 +95,8 @@ struct vgicp_context {
   Pose lin;  // linearized_x (float)
 
   DevBuf<unsigned char> staging;
+  DevBuf<unsigned char> knn_scratch;
+  int knn_mode = 0;  // 0 = hash grid (default), 1 = warp-cooperative scan of the whole cloud, 2 = legacy per-thread scan
   DevBuf<double> partials;
   DevBuf<int> corr_ids;
   unsigned int* d_ticket = nullptr;
@@ -218,7 +220,15 @@ int find_neighbors(vgicp_handle h, Cloud& c, int k) {
   if (k <= 0 || k > kMaxK || k > c.n) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "find_neighbors: need 1 <= k <= min(num_points, 64)");
   CU_TRY(h, c.nbr.reserve((size_t)c.n * k));
   cudaError_t ke = cudaSuccess;
-  KLAUNCH(h, VGICP_PROF_KNN, ke = launch_knn_bruteforce(c.pts.p, c.n, k, c.nbr.p, h->stream));
+  if (h->knn_mode == 2) {  // legacy one-thread-per-query scan, kept for A/B measurements
+    KLAUNCH(h, VGICP_PROF_KNN, ke = launch_knn_bruteforce(c.pts.p, c.n, k, c.nbr.p, h->stream));
+  } else {
+    const size_t need = knn_grid_scratch_bytes(c.n, nullptr, nullptr);
+    CU_TRY(h, h->knn_scratch.reserve(need));
+    int nl = 0;
+    KLAUNCH(h, VGICP_PROF_KNN, ke = launch_knn_grid(c.pts.p, c.n, k, c.nbr.p, h->knn_scratch.p, h->knn_scratch.cap, (h->knn_mode == 1 || c.n < 256) ? 1 : 0, &nl, h->stream));
+    h->launches += nl > 0 ? nl - 1 : 0;
+  }
   CU_TRY(h, ke);
   c.k = k;
   return VGICP_OK;
@@ -441,6 +451,7 @@ int vgicp_destroy(vgicp_handle h) {
   h->map.release();
   h->d_offsets.release();
   h->staging.release();
+  h->knn_scratch.release();
   h->partials.release();
   h->corr_ids.release();
   if (h->d_ticket) cudaFree(h->d_ticket);
@@ -868,6 +879,13 @@ int vgicp_set_target_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, 
   h->target.has_cov = false;
   h->map.built = false;
   return set_cloud(h, h->target, d_xyz, n, stride_bytes, true);
+}
+
+int vgicp_set_knn_mode(vgicp_handle h, int mode) {
+  CHECK_HANDLE(h);
+  if (mode < 0 || mode > 2) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_knn_mode: 0 grid, 1 warp scan, 2 legacy scan");
+  h->knn_mode = mode;
+  return VGICP_OK;
 }
 
 int vgicp_set_profiling(vgicp_handle h, int enable) {

@@ -306,6 +306,294 @@ __global__ void __launch_bounds__(128) k_covariance_rbf(const float4* __restrict
 
 
 // ---------------------------------------------------------------------------------------------------------------
+// Stage 1a': exact k-NN on a multi-level hash grid, one warp per query.
+//
+// Why: lidar clouds are surfaces with a density that falls with range; the 20-NN radius spans 0.2 m .. several metres.
+// A ladder of L uniform grids (cell size s_l = s_max / 2^(L-1-l), s_max = extent/4) is built in three launches
+// (count / allocate / scatter, every point inserted at every level); a query walks the ladder from the finest level
+// and stops at the first level where the 3x3x3 (or 5x5x5) block around its cell provably contains its k nearest
+// neighbours: every point within r*s of the query lies inside the (2r+1)^3 block, so kth_d2 <= (r*s)^2 certifies it.
+// If even the coarsest level cannot certify (tiny clouds, far outliers) the warp scans the whole cloud.
+//
+// Selection: the warp keeps the k best (d2, index) pairs sorted across its lanes (rank r in lane r%32, register
+// r/32); a batch of 32 candidates is loaded coalesced from the cell-sorted copy, lanes whose candidate beats the
+// current worst are inserted one at a time with ballot + shuffle (no shared memory, no divergence between queries).
+// Ties are ordered by index, so the result is the unique ascending (d2, index) list -- identical to the CPU checker.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kGridMaxLevels = 12;
+constexpr unsigned long long kGridEmpty = 0xFFFFFFFFFFFFFFFFULL;
+
+struct GridLevel {
+  unsigned long long* keys;  // [T] packed cell coordinate, kGridEmpty when free
+  int* cnt;                  // [T] points in the cell
+  int* start;                // [T] first index of the cell in `sorted`
+  int* fill;                 // [T] scatter cursor
+  float4* sorted;            // [n] points grouped by cell, original index in .w
+  int* pslot;                // [n] table slot of each point (count pass -> scatter pass)
+};
+
+struct GridArgs {
+  const float4* pts;
+  int n, k, L;
+  unsigned tmask;            // table size - 1 (same for every level)
+  unsigned* bbox_min;        // [3] ordered-uint min xyz (initialised to 0xFFFFFFFF)
+  unsigned* bbox_max;        // [3] ordered-uint max xyz (initialised to 0)
+  int* level_cursor;         // [L]
+  GridLevel lv[kGridMaxLevels];
+  int* nbr;
+};
+
+__device__ __forceinline__ unsigned f2ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void k_grid_bbox(const float4* __restrict__ pts, int n, unsigned* __restrict__ bbox_min, unsigned* __restrict__ bbox_max) {
+  float lo[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+  float hi[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = pts[i];
+    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      atomicMin(&bbox_min[d], f2ord(lo[d]));
+      atomicMax(&bbox_max[d], f2ord(hi[d]));
+    }
+  }
+}
+
+struct GridGeom {
+  float minx, miny, minz;
+  float s_max;
+};
+__device__ __forceinline__ GridGeom grid_geom(const unsigned* __restrict__ bmin, const unsigned* __restrict__ bmax) {
+  GridGeom g;
+  g.minx = ord2f(bmin[0]); g.miny = ord2f(bmin[1]); g.minz = ord2f(bmin[2]);
+  float ex = ord2f(bmax[0]) - g.minx, ey = ord2f(bmax[1]) - g.miny, ez = ord2f(bmax[2]) - g.minz;
+  float e = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-3f));
+  g.s_max = e * 0.25f;
+  return g;
+}
+__device__ __forceinline__ float grid_cell_size(const GridGeom& g, int l, int L) { return ldexpf(g.s_max, l - (L - 1)); }
+__device__ __forceinline__ int3 grid_cell(const GridGeom& g, float inv_s, float x, float y, float z) {
+  return make_int3((int)floorf((x - g.minx) * inv_s), (int)floorf((y - g.miny) * inv_s), (int)floorf((z - g.minz) * inv_s));
+}
+__device__ __forceinline__ unsigned long long grid_key(int x, int y, int z) {  // 21 bits per axis, offset so that -1 is representable
+  return ((unsigned long long)(unsigned)(x + 1024) << 42) | ((unsigned long long)(unsigned)(y + 1024) << 21) | (unsigned long long)(unsigned)(z + 1024);
+}
+__device__ __forceinline__ unsigned grid_hash(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+  return (unsigned)k;
+}
+
+// count pass: thread per (level, point)
+__global__ void k_grid_count(GridArgs a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int l = blockIdx.y;
+  if (i >= a.n) return;
+  GridGeom g = grid_geom(a.bbox_min, a.bbox_max);
+  float inv_s = 1.0f / grid_cell_size(g, l, a.L);
+  float4 p = a.pts[i];
+  int3 c = grid_cell(g, inv_s, p.x, p.y, p.z);
+  unsigned long long key = grid_key(c.x, c.y, c.z);
+  GridLevel lv = a.lv[l];
+  unsigned pos = grid_hash(key) & a.tmask;
+  for (;;) {
+    unsigned long long cur = lv.keys[pos];
+    if (cur == kGridEmpty) {
+      unsigned long long old = atomicCAS(&lv.keys[pos], kGridEmpty, key);
+      cur = (old == kGridEmpty) ? key : old;
+    }
+    if (cur == key) break;
+    pos = (pos + 1) & a.tmask;
+  }
+  atomicAdd(&lv.cnt[pos], 1);
+  lv.pslot[i] = (int)pos;
+}
+
+// allocate pass: thread per (level, slot): carve the cell's range out of the level's sorted array
+__global__ void k_grid_alloc(GridArgs a) {
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  int l = blockIdx.y;
+  if (t > a.tmask) return;
+  GridLevel lv = a.lv[l];
+  int c = lv.cnt[t];
+  if (c > 0) lv.start[t] = atomicAdd(&a.level_cursor[l], c);
+}
+
+// scatter pass: thread per (level, point)
+__global__ void k_grid_scatter(GridArgs a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int l = blockIdx.y;
+  if (i >= a.n) return;
+  GridLevel lv = a.lv[l];
+  int slot = lv.pslot[i];
+  int pos = lv.start[slot] + atomicAdd(&lv.fill[slot], 1);
+  float4 p = a.pts[i];
+  p.w = __int_as_float(i);
+  lv.sorted[pos] = p;
+}
+
+// ---- warp-level sorted top-k (k <= 64): rank r lives in lane r & 31, register r >> 5 ----
+struct WarpTopK {
+  float d0, d1;
+  int i0, i1;
+  float wd;  // current worst (rank k-1), broadcast
+  int wi;
+};
+__device__ __forceinline__ bool pair_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+
+__device__ __forceinline__ void topk_reset(WarpTopK& t) {
+  t.d0 = t.d1 = __int_as_float(0x7f800000);
+  t.i0 = t.i1 = 0x7fffffff;
+  t.wd = __int_as_float(0x7f800000);
+  t.wi = 0x7fffffff;
+}
+
+// all 32 lanes call this with their candidate (valid=false for padding lanes)
+__device__ __forceinline__ void topk_offer(WarpTopK& t, int k, int lane, bool valid, float cd, int ci) {
+  unsigned m = __ballot_sync(0xffffffffu, valid && pair_less(cd, ci, t.wd, t.wi));
+  while (m) {
+    int src = __ffs(m) - 1;
+    m &= m - 1;
+    float nd = __shfl_sync(0xffffffffu, cd, src);
+    int ni = __shfl_sync(0xffffffffu, ci, src);
+    if (!pair_less(nd, ni, t.wd, t.wi)) continue;  // worst moved since the ballot (warp-uniform branch)
+    unsigned b0 = __ballot_sync(0xffffffffu, pair_less(t.d0, t.i0, nd, ni));
+    unsigned b1 = __ballot_sync(0xffffffffu, pair_less(t.d1, t.i1, nd, ni));
+    int p = __popc(b0) + __popc(b1);  // rank of the new entry
+    // shift ranks >= p up by one; rank 31 -> 32 crosses registers
+    float up_d0 = __shfl_up_sync(0xffffffffu, t.d0, 1), up_d1 = __shfl_up_sync(0xffffffffu, t.d1, 1);
+    int up_i0 = __shfl_up_sync(0xffffffffu, t.i0, 1), up_i1 = __shfl_up_sync(0xffffffffu, t.i1, 1);
+    float carry_d = __shfl_sync(0xffffffffu, t.d0, 31);
+    int carry_i = __shfl_sync(0xffffffffu, t.i0, 31);
+    int r1 = 32 + lane;
+    if (r1 > p) { t.d1 = (lane == 0) ? carry_d : up_d1; t.i1 = (lane == 0) ? carry_i : up_i1; }
+    else if (r1 == p) { t.d1 = nd; t.i1 = ni; }
+    if (lane > p) { t.d0 = up_d0; t.i0 = up_i0; }
+    else if (lane == p) { t.d0 = nd; t.i0 = ni; }
+    int kr = k - 1;
+    float w0 = __shfl_sync(0xffffffffu, t.d0, kr & 31), w1 = __shfl_sync(0xffffffffu, t.d1, kr & 31);
+    int x0 = __shfl_sync(0xffffffffu, t.i0, kr & 31), x1 = __shfl_sync(0xffffffffu, t.i1, kr & 31);
+    t.wd = (kr < 32) ? w0 : w1;
+    t.wi = (kr < 32) ? x0 : x1;
+  }
+}
+
+__device__ __forceinline__ float knn_d2(float4 q, float4 t) {  // (dx*dx + dy*dy) + dz*dz, no contraction
+  float dx = __fsub_rn(t.x, q.x), dy = __fsub_rn(t.y, q.y), dz = __fsub_rn(t.z, q.z);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// scan one contiguous run of the cell-sorted array
+__device__ __forceinline__ void scan_run(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int start, int count) {
+  for (int off = 0; off < count; off += 32) {
+    int j = off + lane;
+    bool valid = j < count;
+    float4 c = valid ? __ldg(&sorted[start + j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    topk_offer(t, k, lane, valid, knn_d2(q, c), __float_as_int(c.w));
+  }
+}
+
+__device__ __forceinline__ void probe_cell(const GridLevel& lv, unsigned tmask, int x, int y, int z, int& start, int& count) {
+  count = 0;
+  start = 0;
+  if (x < -1 || y < -1 || z < -1) return;
+  unsigned long long key = grid_key(x, y, z);
+  unsigned pos = grid_hash(key) & tmask;
+  for (;;) {
+    unsigned long long cur = __ldg(&lv.keys[pos]);
+    if (cur == key) { start = __ldg(&lv.start[pos]); count = __ldg(&lv.cnt[pos]); return; }
+    if (cur == kGridEmpty) return;
+    pos = (pos + 1) & tmask;
+  }
+}
+
+// scan all non-empty cells among the (up to 32) probed by the lanes
+__device__ __forceinline__ void scan_lane_cells(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int my_start, int my_count) {
+  unsigned m = __ballot_sync(0xffffffffu, my_count > 0);
+  while (m) {
+    int src = __ffs(m) - 1;
+    m &= m - 1;
+    int st = __shfl_sync(0xffffffffu, my_start, src), cn = __shfl_sync(0xffffffffu, my_count, src);
+    scan_run(t, k, lane, q, sorted, st, cn);
+  }
+}
+
+constexpr int kKnnGridWarps = 8;  // warps (queries) per block
+// nearest-first order of the 3x3x3 block (index = 9*(dx+1) + 3*(dy+1) + (dz+1)): centre, 6 faces, 12 edges, 8 corners
+__constant__ unsigned char kBlockOrder[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25, 0, 2, 6, 8, 18, 20, 24, 26};
+
+__global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid(GridArgs a, int force_bruteforce) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * kKnnGridWarps + (threadIdx.x >> 5);
+  if (w >= a.n) return;
+  // queries in the finest level's cell order: neighbouring warps touch the same cells
+  float4 q = __ldg(&a.lv[0].sorted[w]);
+  const int qi = __float_as_int(q.w);
+  const int k = a.k;
+  WarpTopK t;
+  topk_reset(t);
+  bool done = false;
+  if (!force_bruteforce) {
+    GridGeom g = grid_geom(a.bbox_min, a.bbox_max);
+    // nearest-first cell order inside the 3x3x3 block: centre, faces, edges, corners
+    int dx = 0, dy = 0, dz = 0;
+    if (lane < 27) {
+      int o = kBlockOrder[lane];
+      dx = o / 9 - 1; dy = (o / 3) % 3 - 1; dz = o % 3 - 1;
+    }
+    for (int l = 0; l < a.L && !done; l++) {
+      const float s = grid_cell_size(g, l, a.L);
+      const float inv_s = 1.0f / s;
+      const GridLevel lv = a.lv[l];
+      int3 c = grid_cell(g, inv_s, q.x, q.y, q.z);
+      int st = 0, cn = 0;
+      if (lane < 27) probe_cell(lv, a.tmask, c.x + dx, c.y + dy, c.z + dz, st, cn);
+      int total = cn;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      if (total < k) continue;  // not enough points in the block: coarser level
+      topk_reset(t);
+      scan_lane_cells(t, k, lane, q, lv.sorted, st, cn);
+      const float r1 = s * 0.999f, r2 = 2.0f * s * 0.999f;
+      if (t.wd <= r1 * r1) { done = true; break; }
+      if (t.wd <= r2 * r2) {  // the 5x5x5 shell settles it
+        for (int base = 0; base < 125; base += 32) {
+          int o = base + lane;
+          int sx = o / 25 - 2, sy = (o / 5) % 5 - 2, sz = o % 5 - 2;
+          bool shell = o < 125 && (abs(sx) == 2 || abs(sy) == 2 || abs(sz) == 2);
+          int st2 = 0, cn2 = 0;
+          if (shell) probe_cell(lv, a.tmask, c.x + sx, c.y + sy, c.z + sz, st2, cn2);
+          scan_lane_cells(t, k, lane, q, lv.sorted, st2, cn2);
+        }
+        done = true;
+        break;
+      }
+    }
+  }
+  if (!done) {  // whole cloud (level 0 copy, coalesced)
+    topk_reset(t);
+    scan_run(t, k, lane, q, a.lv[0].sorted, 0, a.n);
+  }
+  int* row = a.nbr + (size_t)qi * k;
+  if (lane < k) row[lane] = t.i0;
+  if (32 + lane < k) row[32 + lane] = t.i1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------------
 size_t knn_smem_bytes(int k) { return sizeof(float4) * kKnnTile + (size_t)k * kKnnThreads * (sizeof(float) + sizeof(int)); }
@@ -318,6 +606,57 @@ cudaError_t launch_knn_bruteforce(const float4* pts, int n, int k, int* nbr, cud
     attr_set = true;
   }
   k_knn_bruteforce<<<(n + kKnnThreads - 1) / kKnnThreads, kKnnThreads, knn_smem_bytes(k), stream>>>(pts, n, k, nbr);
+  return cudaGetLastError();
+}
+
+size_t knn_grid_scratch_bytes(int n, int* levels_out, unsigned* table_size_out) {
+  int L = 8;
+  for (long m = 16384; m * 4 <= (long)n && L < kGridMaxLevels; m *= 4) L++;
+  if (n < 4096) L = 6;
+  unsigned T = 1024;
+  while (T < 2u * (unsigned)n) T <<= 1;
+  if (levels_out) *levels_out = L;
+  if (table_size_out) *table_size_out = T;
+  size_t per_level = (size_t)T * (8 + 4 + 4 + 4) + (size_t)n * (16 + 4);
+  return 4096 + (size_t)L * per_level;
+}
+
+// scratch layout:  [0xFF-filled : bbox min (16 B) | keys of all levels]
+//                  [zero-filled : bbox max (16 B) | level cursors (64 B) | cnt, fill of all levels]
+//                  [uninitialised: start of all levels | sorted copies | pslot]
+cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned char* scratch, size_t scratch_bytes, int force_bruteforce, int* launches, cudaStream_t stream) {
+  int L;
+  unsigned T;
+  size_t need = knn_grid_scratch_bytes(n, &L, &T);
+  if (scratch_bytes < need || (reinterpret_cast<uintptr_t>(scratch) & 15)) return cudaErrorInvalidValue;
+  GridArgs a;
+  a.pts = pts; a.n = n; a.k = k; a.L = L; a.tmask = T - 1; a.nbr = nbr;
+  unsigned char* p = scratch;
+  unsigned char* ff_begin = p;
+  a.bbox_min = reinterpret_cast<unsigned*>(p); p += 16;
+  for (int l = 0; l < L; l++) { a.lv[l].keys = reinterpret_cast<unsigned long long*>(p); p += (size_t)T * 8; }
+  const size_t ff_bytes = (size_t)(p - ff_begin);
+  unsigned char* z_begin = p;
+  a.bbox_max = reinterpret_cast<unsigned*>(p); p += 16;
+  a.level_cursor = reinterpret_cast<int*>(p); p += 64;
+  for (int l = 0; l < L; l++) {
+    a.lv[l].cnt = reinterpret_cast<int*>(p); p += (size_t)T * 4;
+    a.lv[l].fill = reinterpret_cast<int*>(p); p += (size_t)T * 4;
+  }
+  const size_t z_bytes = (size_t)(p - z_begin);
+  for (int l = 0; l < L; l++) { a.lv[l].start = reinterpret_cast<int*>(p); p += (size_t)T * 4; }
+  for (int l = 0; l < L; l++) { a.lv[l].sorted = reinterpret_cast<float4*>(p); p += (size_t)n * 16; }
+  for (int l = 0; l < L; l++) { a.lv[l].pslot = reinterpret_cast<int*>(p); p += (size_t)n * 4; }
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(ff_begin, 0xFF, ff_bytes, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(z_begin, 0, z_bytes, stream)) != cudaSuccess) return e;
+  const int nb = (n + 255) / 256;
+  k_grid_bbox<<<nb < 592 ? nb : 592, 256, 0, stream>>>(pts, n, a.bbox_min, a.bbox_max);
+  k_grid_count<<<dim3(nb, L), 256, 0, stream>>>(a);
+  k_grid_alloc<<<dim3((T + 255) / 256, L), 256, 0, stream>>>(a);
+  k_grid_scatter<<<dim3(nb, L), 256, 0, stream>>>(a);
+  k_knn_grid<<<(n + kKnnGridWarps - 1) / kKnnGridWarps, kKnnGridWarps * 32, 0, stream>>>(a, force_bruteforce);
+  if (launches) *launches = 5;
   return cudaGetLastError();
 }
 

@@ -152,6 +152,9 @@ VGICP_API int vgicp_transform_source(vgicp_handle h, const double T[16], float* 
  * the read is stream-ordered on the handle's stream, the caller keeps the buffer alive until the next synchronising call */
 VGICP_API int vgicp_set_source_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, size_t stride_bytes);
 VGICP_API int vgicp_set_target_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, size_t stride_bytes);
+/* k-NN engine used by find_*_neighbors: 0 = multi-level hash grid (default), 1 = warp-cooperative scan of the whole cloud,
+ * 2 = one-thread-per-query scan (the shape of the reference's brute_force_knn.cu).  All three return identical rows. */
+VGICP_API int vgicp_set_knn_mode(vgicp_handle h, int mode);
 /* per-kernel timing with CUDA events on the handle's stream (off by default; enabling resets the counters) */
 enum {
   VGICP_PROF_UNPACK = 0, VGICP_PROF_KNN = 1, VGICP_PROF_COVARIANCE = 2, VGICP_PROF_VOXELMAP = 3, VGICP_PROF_LINEARIZE = 4, VGICP_PROF_ERROR = 5,

@@ -53,14 +53,43 @@ def test_knn_matches_oracle_exactly(core, prepared):
     assert np.array_equal(got[:, 0], np.arange(len(got)))  # self is neighbour 0 (H6)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("k", [1, 7, 33, 64])
-def test_knn_other_k(core, k):
+def test_knn_other_k(core, k, mode):
+    """All three k-NN engines (hash grid, warp scan, per-thread scan) return the oracle's rows; duplicates tie-break by index."""
     rng = np.random.default_rng(k)
     pts = rng.uniform(-20, 20, size=(1500, 3)).astype(np.float32)
     pts[100:110] = pts[100]  # duplicates: ties broken by index
+    core.set_knn_mode(mode)
     core.set_source_cloud(pts)
     core.find_source_neighbors(k)
-    assert np.array_equal(core.get_source_neighbors(), O.knn(pts, k, "bruteforce"))
+    got = core.get_source_neighbors()
+    core.set_knn_mode(0)
+    assert np.array_equal(got, O.knn(pts, k, "bruteforce"))
+
+
+@pytest.mark.parametrize("shape", ["line", "clusters", "outliers", "tiny", "identical", "17k"])
+def test_knn_grid_hard_cases(core, shape, pair01):
+    """Density extremes for the multi-level grid: 1-D line, tight clusters far apart, far outliers, tiny clouds, all-equal points."""
+    rng = np.random.default_rng(11)
+    if shape == "line":
+        pts = np.zeros((3000, 3), dtype=np.float32)
+        pts[:, 0] = np.sort(rng.uniform(0, 500, 3000))
+    elif shape == "clusters":
+        pts = np.concatenate([rng.normal(c, 0.01, size=(400, 3)) for c in rng.uniform(-300, 300, size=(8, 3))]).astype(np.float32)
+    elif shape == "outliers":
+        pts = rng.normal(0, 1.0, size=(4000, 3)).astype(np.float32)
+        pts[:5] = rng.uniform(2000, 5000, size=(5, 3))
+    elif shape == "tiny":
+        pts = rng.uniform(-1, 1, size=(23, 3)).astype(np.float32)
+    elif shape == "identical":
+        pts = np.tile(np.array([[1.5, -2.0, 0.25]], dtype=np.float32), (700, 1))
+    else:
+        pts = pair01[0]
+    k = 20
+    core.set_source_cloud(pts)
+    core.find_source_neighbors(k)
+    assert np.array_equal(core.get_source_neighbors(), O.knn(pts, k, "kdtree" if len(pts) > 5000 else "bruteforce"))
 
 
 def test_raw_covariance_bit_exact(core, prepared):
