@@ -357,20 +357,33 @@ int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H) {
   a.offsets = h->d_offsets.p; a.n_off = (int)h->h_offsets.size(); a.res = m.res;
   a.Tlin = h->lin; a.Teval = Teval;
   a.partials = h->partials.p; a.ticket = h->d_ticket; a.out = h->d_out;
-  int grid = blocks_for(s.n > 0 ? s.n : 1, kLinThreads);
+  // lanes per source point: split the neighbour cells of a point over G lanes while the cloud is too small to fill the
+  // GPU with one thread per point (latency-bound regime); one lane per point once it is large (ALU/bandwidth-bound regime)
+  const int n_off = (int)h->h_offsets.size();
+  const bool wide = s.n < 400000 && n_off > 1;
+  const int G = !wide ? 1 : (n_off <= 7 ? 4 : 8);
+  long long tasks = (long long)(s.n > 0 ? s.n : 1) * G;
+  int grid = (int)((tasks + kLinThreads - 1) / kLinThreads);
   if (grid > kLinMaxBlocks) grid = kLinMaxBlocks;
-#define LAUNCH_LIN(MODE)                                                            \
-  do {                                                                              \
-    if (want_H) k_linearize<MODE, true><<<grid, kLinThreads, 0, h->stream>>>(a);    \
-    else k_linearize<MODE, false><<<grid, kLinThreads, 0, h->stream>>>(a);          \
+#define LAUNCH_LIN_G(MODE, GG)                                                           \
+  do {                                                                                   \
+    if (want_H) k_linearize<MODE, true, GG><<<grid, kLinThreads, 0, h->stream>>>(a);     \
+    else k_linearize<MODE, false, GG><<<grid, kLinThreads, 0, h->stream>>>(a);           \
+  } while (0)
+#define LAUNCH_LIN(MODE)                 \
+  do {                                   \
+    if (G == 8) LAUNCH_LIN_G(MODE, 8);   \
+    else if (G == 4) LAUNCH_LIN_G(MODE, 4); \
+    else LAUNCH_LIN_G(MODE, 1);          \
   } while (0)
   prof_begin(h, want_H ? VGICP_PROF_LINEARIZE : VGICP_PROF_ERROR);
   switch (h->offset_mode) {
-    case 1: LAUNCH_LIN(1); break;
+    case 1: LAUNCH_LIN_G(1, 1); break;
     case 7: LAUNCH_LIN(7); break;
     case 27: LAUNCH_LIN(27); break;
     default: LAUNCH_LIN(0); break;
   }
+#undef LAUNCH_LIN_G
 #undef LAUNCH_LIN
   prof_end(h);
   h->launches++;
@@ -418,7 +431,7 @@ int vgicp_create(int device, vgicp_handle* out) {
   DeviceGuard g(device);
   // the kernel image is sm_100a only: fail loudly on anything else instead of falling back
   cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, k_linearize<1, true>) != cudaSuccess) {
+  if (cudaFuncGetAttributes(&fa, k_linearize<1, true, 1>) != cudaSuccess) {
     cudaGetLastError();
     delete h;
     return VGICP_ERR_NO_DEVICE;

@@ -286,42 +286,64 @@ struct PointAcc {
   float err;
 };
 
+// one correspondence: S = C_B + R C_A R^T (symmetric), M = S^-1 by cofactors (Eigen Matrix3f::inverse), w = sqrt(n);
+// `hit` = false contributes exactly zero (the voxel record read for a miss is voxel 0, only there to keep the load
+// unconditional so that all loads of a lane can be in flight together).
 template <bool WANT_H>
-__device__ __forceinline__ void accumulate_voxel(const VoxelRec* __restrict__ vox, int id, const float* rcr, float3 pe, PointAcc<WANT_H>& acc) {
-  const float4* vr = reinterpret_cast<const float4*>(vox + id);
-  float4 mn = __ldg(vr), c0 = __ldg(vr + 1), c1 = __ldg(vr + 2);
+__device__ __forceinline__ void accumulate_voxel(float4 mn, float4 c0, float4 c1, bool hit, const float* rcr, float3 pe, PointAcc<WANT_H>& acc) {
   int np = __float_as_int(mn.w);
-  if (WANT_H && np <= 0) return;  // compute_derivatives.cu:62-64
-  // S = C_B + R C_A R^T (symmetric), M = S^-1 by cofactors (Eigen Matrix3f::inverse)
+  if (WANT_H && np <= 0) hit = false;  // compute_derivatives.cu:62-64
   float a = c0.x + rcr[0], b = c0.y + rcr[1], c = c0.z + rcr[2], d = c0.w + rcr[3], e = c1.x + rcr[4], f = c1.y + rcr[5];
   float k00 = d * f - e * e, k01 = c * e - b * f, k02 = b * e - c * d;
   float det = (a * k00 + b * k01) + c * k02;
   float id_ = 1.0f / det;
   float m00 = k00 * id_, m01 = k01 * id_, m02 = k02 * id_;
   float m11 = (a * f - c * c) * id_, m12 = (b * c - a * e) * id_, m22 = (a * d - b * b) * id_;
-  float w = sqrtf((float)np);
+  float w = hit ? sqrtf((float)np) : 0.0f;
   float ex = mn.x - pe.x, ey = mn.y - pe.y, ez = mn.z - pe.z;
   float mex = (m00 * ex + m01 * ey) + m02 * ez;
   float mey = (m01 * ex + m11 * ey) + m12 * ez;
   float mez = (m02 * ex + m12 * ey) + m22 * ez;
-  acc.err += w * ((ex * mex + ey * mey) + ez * mez);
-  if (WANT_H) {
-    acc.m[0] += w * m00; acc.m[1] += w * m01; acc.m[2] += w * m02; acc.m[3] += w * m11; acc.m[4] += w * m12; acc.m[5] += w * m22;
-    acc.v[0] += w * mex; acc.v[1] += w * mey; acc.v[2] += w * mez;
+  if (hit) {
+    acc.err += w * ((ex * mex + ey * mey) + ez * mez);
+    if (WANT_H) {
+      acc.m[0] += w * m00; acc.m[1] += w * m01; acc.m[2] += w * m02; acc.m[3] += w * m11; acc.m[4] += w * m12; acc.m[5] += w * m22;
+      acc.v[0] += w * mex; acc.v[1] += w * mey; acc.v[2] += w * mez;
+    }
   }
 }
 
-// MODE: 0 = offsets from memory (DIRECT_RADIUS or anything), 1 / 7 / 27 = the reference's fixed tables generated in
-// registers, for 27 with the x/y prefixes of the hash shared between neighbours.
-template <int MODE, bool WANT_H>
+// neighbour offset number o of the reference's fixed tables (fast_vgicp_cuda.cu:57-74)
+template <int MODE>
+__device__ __forceinline__ int3 fixed_offset(int o) {
+  if (MODE == 27) return make_int3(o / 9 - 1, (o / 3) % 3 - 1, o % 3 - 1);  // i-major
+  if (MODE == 7) {
+    // {0,0,0},{1,0,0},{-1,0,0},{0,1,0},{0,-1,0},{0,0,1},{0,0,-1}
+    int axis = (o - 1) >> 1, sgn = (o & 1) ? 1 : -1;
+    return make_int3(o > 0 && axis == 0 ? sgn : 0, o > 0 && axis == 1 ? sgn : 0, o > 0 && axis == 2 ? sgn : 0);
+  }
+  return make_int3(0, 0, 0);
+}
+
+// MODE: 0 = offsets from memory (DIRECT_RADIUS or anything), 1 / 7 / 27 = the reference's fixed tables.
+// G lanes share one source point and split its neighbour cells (lane s takes offsets s, s+G, ...): at 17k points a
+// one-thread-per-point mapping leaves one warp per scheduler and 27 serial dependent probes per thread; with G = 8 the
+// probes of a lane (<= 4) are issued together and the grid has 8x the warps to hide the L2 latency.
+template <int MODE, bool WANT_H, int G>
 __global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
   constexpr int NV = WANT_H ? kLinValues : 1;
+  constexpr int NOFF = MODE == 0 ? 0 : MODE;
+  constexpr int CELLS = MODE == 0 ? 4 : ((NOFF + G - 1) / G < 4 ? (NOFF + G - 1) / G : 4);  // cells per lane per pass (loads in flight)
   float sum[NV];
 #pragma unroll
   for (int i = 0; i < NV; i++) sum[i] = 0.f;
 
   const Pose Tl = a.Tlin, Te = a.Teval;
-  for (int i = blockIdx.x * kLinThreads + threadIdx.x; i < a.n; i += gridDim.x * kLinThreads) {
+  const int n_off = MODE == 0 ? a.n_off : NOFF;
+  const long long n_tasks = (long long)a.n * G;
+  for (long long task = (long long)blockIdx.x * kLinThreads + threadIdx.x; task < n_tasks; task += (long long)gridDim.x * kLinThreads) {
+    const int i = (int)(task / G);
+    const int sub = (int)(task % G);
     float4 p = a.pts[i];
     float4 ca = a.covA[i];
     float2 cb = a.covB[i];
@@ -352,50 +374,51 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
     acc.v[0] = acc.v[1] = acc.v[2] = 0.f;
     acc.err = 0.f;
 
-    if (MODE == 27) {
-      uint64_t kx[3], ky[3], kz[3];
+    for (int o0 = sub; o0 < n_off; o0 += G * CELLS) {
+      // phase 1: all first-probe bucket loads of this lane in flight together
+      int cx[CELLS], cy[CELLS], cz[CELLS];
+      unsigned pos[CELLS];
+      int4 bk[CELLS];
+      bool valid[CELLS];
 #pragma unroll
-      for (int d = 0; d < 3; d++) {
-        kx[d] = hash_mix((uint64_t)(int64_t)(bx + d - 1));
-        ky[d] = hash_mix((uint64_t)(int64_t)(by + d - 1));
-        kz[d] = hash_mix((uint64_t)(int64_t)(bz + d - 1));
-      }
-#pragma unroll
-      for (int ix = 0; ix < 3; ix++) {
-        uint64_t hx = hash_fold(0, kx[ix]);
-#pragma unroll
-        for (int iy = 0; iy < 3; iy++) {
-          uint64_t hy = hash_fold(hx, ky[iy]);
-#pragma unroll
-          for (int iz = 0; iz < 3; iz++) {
-            uint64_t h = hash_fold(hy, kz[iz]);
-            int id = lookup_voxel(a.buckets, a.mask, a.max_scan, h, bx + ix - 1, by + iy - 1, bz + iz - 1);
-            if (id >= 0) accumulate_voxel<WANT_H>(a.vox, id, rcr, pe, acc);
-          }
+      for (int j = 0; j < CELLS; j++) {
+        const int o = o0 + j * G;
+        valid[j] = o < n_off;
+        int3 off;
+        if (MODE == 0) {
+          int4 t4 = __ldg(&a.offsets[valid[j] ? o : 0]);
+          off = make_int3(t4.x, t4.y, t4.z);
+        } else {
+          off = fixed_offset<MODE>(valid[j] ? o : 0);
         }
+        cx[j] = bx + off.x; cy[j] = by + off.y; cz[j] = bz + off.z;
+        pos[j] = (unsigned)(vector3i_hash(cx[j], cy[j], cz[j]) & a.mask);
+        bk[j] = __ldg(&a.buckets[pos[j]]);
       }
-    } else if (MODE == 7) {
-      const int ox[7] = {0, 1, -1, 0, 0, 0, 0}, oy[7] = {0, 0, 0, 1, -1, 0, 0}, oz[7] = {0, 0, 0, 0, 0, 1, -1};
+      // phase 2: resolve (further probes are rare: the table is <= ~50% full), then unconditional voxel loads
+      int id[CELLS];
+      float4 mn[CELLS], c0[CELLS], c1[CELLS];
 #pragma unroll
-      for (int o = 0; o < 7; o++) {
-        int cx = bx + ox[o], cy = by + oy[o], cz = bz + oz[o];
-        int id = lookup_voxel(a.buckets, a.mask, a.max_scan, vector3i_hash(cx, cy, cz), cx, cy, cz);
-        if (id >= 0) accumulate_voxel<WANT_H>(a.vox, id, rcr, pe, acc);
+      for (int j = 0; j < CELLS; j++) {
+        int4 b = bk[j];
+        int found = -1;
+        for (int s = 0; s < a.max_scan; s++) {  // find_voxel_correspondences.cu:39-51
+          if (b.w < 0) break;
+          if (b.x == cx[j] && b.y == cy[j] && b.z == cz[j]) { found = b.w; break; }
+          pos[j] = (pos[j] + 1) & a.mask;
+          if (s + 1 < a.max_scan) b = __ldg(&a.buckets[pos[j]]);
+        }
+        id[j] = valid[j] ? found : -1;
+        const float4* vr = reinterpret_cast<const float4*>(a.vox + (id[j] >= 0 ? id[j] : 0));
+        mn[j] = __ldg(vr); c0[j] = __ldg(vr + 1); c1[j] = __ldg(vr + 2);
       }
-    } else if (MODE == 1) {
-      int id = lookup_voxel(a.buckets, a.mask, a.max_scan, vector3i_hash(bx, by, bz), bx, by, bz);
-      if (id >= 0) accumulate_voxel<WANT_H>(a.vox, id, rcr, pe, acc);
-    } else {
-      for (int o = 0; o < a.n_off; o++) {
-        int4 off = __ldg(&a.offsets[o]);
-        int cx = bx + off.x, cy = by + off.y, cz = bz + off.z;
-        int id = lookup_voxel(a.buckets, a.mask, a.max_scan, vector3i_hash(cx, cy, cz), cx, cy, cz);
-        if (id >= 0) accumulate_voxel<WANT_H>(a.vox, id, rcr, pe, acc);
-      }
+#pragma unroll
+      for (int j = 0; j < CELLS; j++) accumulate_voxel<WANT_H>(mn[j], c0[j], c1[j], id[j] >= 0, rcr, pe, acc);
     }
 
     if (WANT_H) {
       // B = S*Msum (3x3), A = -B*S, with S = skew(pe);  H = [[A, B],[B^T, Msum]],  b = [-(pe x v); -v]
+      // (linear in Msum and v, so every lane applies J to its own partial sums)
       const float* M = acc.m;  // xx xy xz yy yz zz
       float Mf[9] = {M[0], M[1], M[2], M[1], M[3], M[4], M[2], M[4], M[5]};
       float B[9];
@@ -459,9 +482,19 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
   {
     const int v = threadIdx.x & 31, chain = threadIdx.x >> 5;  // kLinThreads == 128 -> 4 chains
     if (v < NV) {
+      // ld.global.cg: coherent at L2 (the partials were written by other SMs), 16 independent loads in flight per
+      // round -- a dependent load->add chain over 148 blocks costs ~25 us of serialised L2 latency
       double s = 0.0;
-      const volatile double* part = a.partials;
-      for (unsigned b = chain; b < gridDim.x; b += 4) s += part[(size_t)b * kLinValues + v];
+      const double* part = a.partials + v;
+      unsigned b = chain;
+      for (; b + 4 * 15 < gridDim.x; b += 4 * 16) {
+        double t[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) t[u] = __ldcg(part + (size_t)(b + 4 * u) * kLinValues);
+#pragma unroll
+        for (int u = 0; u < 16; u++) s += t[u];
+      }
+      for (; b < gridDim.x; b += 4) s += __ldcg(part + (size_t)b * kLinValues);
       fin[chain][v] = s;
     }
   }

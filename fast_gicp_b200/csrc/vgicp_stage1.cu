@@ -339,6 +339,10 @@ struct GridArgs {
   unsigned* bbox_min;        // [3] ordered-uint min xyz (initialised to 0xFFFFFFFF)
   unsigned* bbox_max;        // [3] ordered-uint max xyz (initialised to 0)
   int* level_cursor;         // [L]
+  int* query_cursor;         // work counter of the query kernel
+  int* heavy_count;          // number of queries deferred to the block-cooperative kernel
+  int* heavy_cursor;         // its work counter
+  int2* heavy_queue;         // [n] (position in lv[0].sorted, level to resume at)
   GridLevel lv[kGridMaxLevels];
   int* nbr;
 };
@@ -398,55 +402,83 @@ __device__ __forceinline__ unsigned grid_hash(unsigned long long k) {
   return (unsigned)k;
 }
 
-// count pass: thread per (level, point)
+// count pass: thread per (level, point).  Consecutive points are spatially coherent (scan order), so most lanes of a
+// warp fall into the same cell, above all on the coarse levels: lanes with equal keys elect a leader that does the
+// table probe and one atomicAdd for the group (same-address atomics serialise in L2).
 __global__ void k_grid_count(GridArgs a) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int l = blockIdx.y;
-  if (i >= a.n) return;
+  const bool active = i < a.n;
   GridGeom g = grid_geom(a.bbox_min, a.bbox_max);
   float inv_s = 1.0f / grid_cell_size(g, l, a.L);
-  float4 p = a.pts[i];
+  float4 p = a.pts[active ? i : 0];
   int3 c = grid_cell(g, inv_s, p.x, p.y, p.z);
-  unsigned long long key = grid_key(c.x, c.y, c.z);
+  unsigned long long key = active ? grid_key(c.x, c.y, c.z) : kGridEmpty;
   GridLevel lv = a.lv[l];
-  unsigned pos = grid_hash(key) & a.tmask;
-  for (;;) {
-    unsigned long long cur = lv.keys[pos];
-    if (cur == kGridEmpty) {
-      unsigned long long old = atomicCAS(&lv.keys[pos], kGridEmpty, key);
-      cur = (old == kGridEmpty) ? key : old;
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  unsigned pos = 0;
+  if (active && lane == leader) {
+    pos = grid_hash(key) & a.tmask;
+    for (;;) {
+      unsigned long long cur = lv.keys[pos];
+      if (cur == kGridEmpty) {
+        unsigned long long old = atomicCAS(&lv.keys[pos], kGridEmpty, key);
+        cur = (old == kGridEmpty) ? key : old;
+      }
+      if (cur == key) break;
+      pos = (pos + 1) & a.tmask;
     }
-    if (cur == key) break;
-    pos = (pos + 1) & a.tmask;
+    atomicAdd(&lv.cnt[pos], __popc(peers));
   }
-  atomicAdd(&lv.cnt[pos], 1);
-  lv.pslot[i] = (int)pos;
+  pos = __shfl_sync(0xffffffffu, pos, leader);
+  if (active) lv.pslot[i] = (int)pos;
 }
 
-// allocate pass: thread per (level, slot): carve the cell's range out of the level's sorted array
+// allocate pass: thread per (level, slot): carve the cell's range out of the level's sorted array (one atomic per warp)
 __global__ void k_grid_alloc(GridArgs a) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   int l = blockIdx.y;
-  if (t > a.tmask) return;
   GridLevel lv = a.lv[l];
-  int c = lv.cnt[t];
-  if (c > 0) lv.start[t] = atomicAdd(&a.level_cursor[l], c);
+  const int lane = threadIdx.x & 31;
+  int c = (t <= a.tmask) ? lv.cnt[t] : 0;
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  int base = 0;
+  if (lane == 31) base = atomicAdd(&a.level_cursor[l], total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (c > 0) lv.start[t] = base + incl - c;
 }
 
-// scatter pass: thread per (level, point)
+// scatter pass: thread per (level, point), one cursor atomic per group of lanes sharing a cell
 __global__ void k_grid_scatter(GridArgs a) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int l = blockIdx.y;
-  if (i >= a.n) return;
+  const bool active = i < a.n;
   GridLevel lv = a.lv[l];
-  int slot = lv.pslot[i];
-  int pos = lv.start[slot] + atomicAdd(&lv.fill[slot], 1);
+  const int lane = threadIdx.x & 31;
+  int slot = active ? lv.pslot[i] : -1 - lane;  // inactive lanes get unique keys
+  const unsigned peers = __match_any_sync(0xffffffffu, slot);
+  const int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (active && lane == leader) base = lv.start[slot] + atomicAdd(&lv.fill[slot], __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (!active) return;
+  int rank = __popc(peers & ((1u << lane) - 1u));
   float4 p = a.pts[i];
   p.w = __int_as_float(i);
-  lv.sorted[pos] = p;
+  lv.sorted[base + rank] = p;
 }
 
-// ---- warp-level sorted top-k (k <= 64): rank r lives in lane r & 31, register r >> 5 ----
+// ---- warp-level sorted top-k (k <= 64): rank r lives in lane r & 31, register r >> 5.  WIDE=false (k <= 32) keeps a
+// single register set: an insertion is 2 broadcasts + 1 ballot + 2 shuffle-ups + 2 broadcasts. ----
 struct WarpTopK {
   float d0, d1;
   int i0, i1;
@@ -462,9 +494,46 @@ __device__ __forceinline__ void topk_reset(WarpTopK& t) {
   t.wi = 0x7fffffff;
 }
 
+// compare-exchange step of a bitonic network over the 32 lanes: lane keeps the smaller pair when keep_min
+__device__ __forceinline__ void cmpx(float& d, int& i, int stride, bool keep_min) {
+  float od = __shfl_xor_sync(0xffffffffu, d, stride);
+  int oi = __shfl_xor_sync(0xffffffffu, i, stride);
+  bool o_less = pair_less(od, oi, d, i);
+  bool swap = keep_min ? o_less : pair_less(d, i, od, oi);
+  if (swap) { d = od; i = oi; }
+}
+
+// Merge a batch of 32 candidates into the sorted list (k <= 32): bitonic-sort the batch (15 steps), take the element-wise
+// minimum with the reversed list (the 32 smallest of the 64, a bitonic sequence), bitonic-merge (5 steps).  ~170
+// instructions however many candidates make it into the list, against ~35 per single insertion.
+__device__ __forceinline__ void topk_merge32(WarpTopK& t, int k, int lane, float cd, int ci) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      bool up = (lane & size) == 0 || size == 32;
+      bool lower = (lane & stride) == 0;
+      cmpx(cd, ci, stride, lower == up);
+    }
+  }
+  float rd = __shfl_sync(0xffffffffu, cd, 31 - lane);
+  int ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
+  if (pair_less(rd, ri, t.d0, t.i0)) { t.d0 = rd; t.i0 = ri; }
+#pragma unroll
+  for (int stride = 16; stride > 0; stride >>= 1) cmpx(t.d0, t.i0, stride, (lane & stride) == 0);
+  t.wd = __shfl_sync(0xffffffffu, t.d0, k - 1);
+  t.wi = __shfl_sync(0xffffffffu, t.i0, k - 1);
+}
+
 // all 32 lanes call this with their candidate (valid=false for padding lanes)
+template <bool WIDE>
 __device__ __forceinline__ void topk_offer(WarpTopK& t, int k, int lane, bool valid, float cd, int ci) {
-  unsigned m = __ballot_sync(0xffffffffu, valid && pair_less(cd, ci, t.wd, t.wi));
+  const bool pass = valid && pair_less(cd, ci, t.wd, t.wi);
+  unsigned m = __ballot_sync(0xffffffffu, pass);
+  if (!WIDE && __popc(m) > 4) {  // many entrants: one sort-merge instead of one insertion each
+    topk_merge32(t, k, lane, pass ? cd : __int_as_float(0x7f800000), pass ? ci : 0x7fffffff);
+    return;
+  }
   while (m) {
     int src = __ffs(m) - 1;
     m &= m - 1;
@@ -472,23 +541,32 @@ __device__ __forceinline__ void topk_offer(WarpTopK& t, int k, int lane, bool va
     int ni = __shfl_sync(0xffffffffu, ci, src);
     if (!pair_less(nd, ni, t.wd, t.wi)) continue;  // worst moved since the ballot (warp-uniform branch)
     unsigned b0 = __ballot_sync(0xffffffffu, pair_less(t.d0, t.i0, nd, ni));
-    unsigned b1 = __ballot_sync(0xffffffffu, pair_less(t.d1, t.i1, nd, ni));
-    int p = __popc(b0) + __popc(b1);  // rank of the new entry
-    // shift ranks >= p up by one; rank 31 -> 32 crosses registers
-    float up_d0 = __shfl_up_sync(0xffffffffu, t.d0, 1), up_d1 = __shfl_up_sync(0xffffffffu, t.d1, 1);
-    int up_i0 = __shfl_up_sync(0xffffffffu, t.i0, 1), up_i1 = __shfl_up_sync(0xffffffffu, t.i1, 1);
-    float carry_d = __shfl_sync(0xffffffffu, t.d0, 31);
-    int carry_i = __shfl_sync(0xffffffffu, t.i0, 31);
-    int r1 = 32 + lane;
-    if (r1 > p) { t.d1 = (lane == 0) ? carry_d : up_d1; t.i1 = (lane == 0) ? carry_i : up_i1; }
-    else if (r1 == p) { t.d1 = nd; t.i1 = ni; }
+    int p = __popc(b0);  // rank of the new entry
+    float up_d0 = __shfl_up_sync(0xffffffffu, t.d0, 1);
+    int up_i0 = __shfl_up_sync(0xffffffffu, t.i0, 1);
+    const int kr = k - 1;
+    if (WIDE) {
+      unsigned b1 = __ballot_sync(0xffffffffu, pair_less(t.d1, t.i1, nd, ni));
+      p += __popc(b1);
+      float up_d1 = __shfl_up_sync(0xffffffffu, t.d1, 1);
+      int up_i1 = __shfl_up_sync(0xffffffffu, t.i1, 1);
+      float carry_d = __shfl_sync(0xffffffffu, t.d0, 31);  // rank 31 -> 32 crosses registers
+      int carry_i = __shfl_sync(0xffffffffu, t.i0, 31);
+      int r1 = 32 + lane;
+      if (r1 > p) { t.d1 = (lane == 0) ? carry_d : up_d1; t.i1 = (lane == 0) ? carry_i : up_i1; }
+      else if (r1 == p) { t.d1 = nd; t.i1 = ni; }
+    }
     if (lane > p) { t.d0 = up_d0; t.i0 = up_i0; }
     else if (lane == p) { t.d0 = nd; t.i0 = ni; }
-    int kr = k - 1;
-    float w0 = __shfl_sync(0xffffffffu, t.d0, kr & 31), w1 = __shfl_sync(0xffffffffu, t.d1, kr & 31);
-    int x0 = __shfl_sync(0xffffffffu, t.i0, kr & 31), x1 = __shfl_sync(0xffffffffu, t.i1, kr & 31);
-    t.wd = (kr < 32) ? w0 : w1;
-    t.wi = (kr < 32) ? x0 : x1;
+    if (WIDE) {
+      float w0 = __shfl_sync(0xffffffffu, t.d0, kr & 31), w1 = __shfl_sync(0xffffffffu, t.d1, kr & 31);
+      int x0 = __shfl_sync(0xffffffffu, t.i0, kr & 31), x1 = __shfl_sync(0xffffffffu, t.i1, kr & 31);
+      t.wd = (kr < 32) ? w0 : w1;
+      t.wi = (kr < 32) ? x0 : x1;
+    } else {
+      t.wd = __shfl_sync(0xffffffffu, t.d0, kr);
+      t.wi = __shfl_sync(0xffffffffu, t.i0, kr);
+    }
   }
 }
 
@@ -497,13 +575,22 @@ __device__ __forceinline__ float knn_d2(float4 q, float4 t) {  // (dx*dx + dy*dy
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// scan one contiguous run of the cell-sorted array
+// scan one contiguous run of the cell-sorted array (whole-cloud fallback), four loads in flight
+template <bool WIDE>
 __device__ __forceinline__ void scan_run(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int start, int count) {
-  for (int off = 0; off < count; off += 32) {
-    int j = off + lane;
-    bool valid = j < count;
-    float4 c = valid ? __ldg(&sorted[start + j]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    topk_offer(t, k, lane, valid, knn_d2(q, c), __float_as_int(c.w));
+  constexpr int U = 4;
+  for (int off = 0; off < count; off += 32 * U) {
+    float4 c[U];
+    bool valid[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int j = off + u * 32 + lane;
+      valid[u] = j < count;
+      c[u] = valid[u] ? __ldg(&sorted[start + j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (off + u * 32 < count) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w));
   }
 }
 
@@ -521,76 +608,240 @@ __device__ __forceinline__ void probe_cell(const GridLevel& lv, unsigned tmask, 
   }
 }
 
-// scan all non-empty cells among the (up to 32) probed by the lanes
+// scan the points of the (up to 32) cells probed by the lanes.  Cells are small (~5 points on the level that wins), so the
+// candidates of all cells are flattened into one index space (prefix sum of the counts across lanes) and consumed in
+// full 32-wide batches; each lane finds the cell of its candidate with a 5-step binary search over the lanes' prefix
+// values.  Four batches (loads) are kept in flight: a sparse query can own thousands of candidates and a single warp
+// is latency-bound.
+template <bool WIDE>
 __device__ __forceinline__ void scan_lane_cells(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int my_start, int my_count) {
-  unsigned m = __ballot_sync(0xffffffffu, my_count > 0);
-  while (m) {
-    int src = __ffs(m) - 1;
-    m &= m - 1;
-    int st = __shfl_sync(0xffffffffu, my_start, src), cn = __shfl_sync(0xffffffffu, my_count, src);
-    scan_run(t, k, lane, q, sorted, st, cn);
+  int incl = my_count;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  const int excl = incl - my_count;
+  constexpr int U = 4;
+  for (int base = 0; base < total; base += 32 * U) {
+    float4 c[U];
+    bool valid[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int j = base + u * 32 + lane;
+      valid[u] = j < total;
+      c[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (base + u * 32 < total) {  // warp-uniform
+        int cell = 0;  // largest lane index whose exclusive prefix is <= j (runs of equal prefixes end at the non-empty cell)
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          int e = __shfl_sync(0xffffffffu, excl, (cell + step) & 31);
+          if (e <= j) cell += step;
+        }
+        int st = __shfl_sync(0xffffffffu, my_start, cell);
+        int ex = __shfl_sync(0xffffffffu, excl, cell);
+        if (valid[u]) c[u] = __ldg(&sorted[st + (j - ex)]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (base + u * 32 < total) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w));
+    }
   }
 }
 
-constexpr int kKnnGridWarps = 8;  // warps (queries) per block
+// the same scans with the batches dealt round-robin to `nw` cooperating warps (warp `wi` takes batches wi, wi+nw, ...)
+template <bool WIDE>
+__device__ __forceinline__ void scan_lane_cells_strided(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int my_start, int my_count, int wi, int nw) {
+  int incl = my_count;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  const int excl = incl - my_count;
+  constexpr int U = 4;
+  for (int base = wi * 32; base < total; base += 32 * U * nw) {
+    float4 c[U];
+    bool valid[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int b0 = base + u * 32 * nw;
+      const int j = b0 + lane;
+      valid[u] = j < total;
+      c[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b0 < total) {
+        int cell = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          int e = __shfl_sync(0xffffffffu, excl, (cell + step) & 31);
+          if (e <= j) cell += step;
+        }
+        int st = __shfl_sync(0xffffffffu, my_start, cell);
+        int ex = __shfl_sync(0xffffffffu, excl, cell);
+        if (valid[u]) c[u] = __ldg(&sorted[st + (j - ex)]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (base + u * 32 * nw < total) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w));
+  }
+}
+
+template <bool WIDE>
+__device__ __forceinline__ void scan_run_strided(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int start, int count, int wi, int nw) {
+  constexpr int U = 4;
+  for (int off = wi * 32; off < count; off += 32 * U * nw) {
+    float4 c[U];
+    bool valid[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int j = off + u * 32 * nw + lane;
+      valid[u] = j < count;
+      c[u] = valid[u] ? __ldg(&sorted[start + j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (off + u * 32 * nw < count) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w));
+  }
+}
+
+constexpr int kKnnGridWarps = 8;      // warps (queries) per block
+constexpr int kHeavyCandidates = 768; // blocks with more candidates than this go to the block-cooperative kernel
 // nearest-first order of the 3x3x3 block (index = 9*(dx+1) + 3*(dy+1) + (dz+1)): centre, 6 faces, 12 edges, 8 corners
 __constant__ unsigned char kBlockOrder[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25, 0, 2, 6, 8, 18, 20, 24, 26};
 
+// Persistent warps pull queries from a global counter (the cost of a query varies by >10x between dense and sparse
+// regions, and queries are visited in cell order, so static blocks would leave a long tail).
+template <bool WIDE>
 __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid(GridArgs a, int force_bruteforce) {
   const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * kKnnGridWarps + (threadIdx.x >> 5);
-  if (w >= a.n) return;
-  // queries in the finest level's cell order: neighbouring warps touch the same cells
-  float4 q = __ldg(&a.lv[0].sorted[w]);
-  const int qi = __float_as_int(q.w);
   const int k = a.k;
-  WarpTopK t;
-  topk_reset(t);
-  bool done = false;
-  if (!force_bruteforce) {
-    GridGeom g = grid_geom(a.bbox_min, a.bbox_max);
-    // nearest-first cell order inside the 3x3x3 block: centre, faces, edges, corners
-    int dx = 0, dy = 0, dz = 0;
-    if (lane < 27) {
-      int o = kBlockOrder[lane];
-      dx = o / 9 - 1; dy = (o / 3) % 3 - 1; dz = o % 3 - 1;
-    }
-    for (int l = 0; l < a.L && !done; l++) {
-      const float s = grid_cell_size(g, l, a.L);
-      const float inv_s = 1.0f / s;
-      const GridLevel lv = a.lv[l];
-      int3 c = grid_cell(g, inv_s, q.x, q.y, q.z);
-      int st = 0, cn = 0;
-      if (lane < 27) probe_cell(lv, a.tmask, c.x + dx, c.y + dy, c.z + dz, st, cn);
-      int total = cn;
+  GridGeom g = grid_geom(a.bbox_min, a.bbox_max);
+  // nearest-first cell order inside the 3x3x3 block: centre, faces, edges, corners
+  int dx = 0, dy = 0, dz = 0;
+  if (lane < 27) {
+    int o = kBlockOrder[lane];
+    dx = o / 9 - 1; dy = (o / 3) % 3 - 1; dz = o % 3 - 1;
+  }
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(a.query_cursor, 1);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= a.n) return;
+    // queries in the finest level's cell order: neighbouring warps touch the same cells
+    float4 q = __ldg(&a.lv[0].sorted[w]);
+    const int qi = __float_as_int(q.w);
+    WarpTopK t;
+    topk_reset(t);
+    bool done = false, deferred = false;
+    if (!force_bruteforce) {
+      for (int l = 0; l < a.L && !done; l++) {
+        const float s = grid_cell_size(g, l, a.L);
+        const float inv_s = 1.0f / s;
+        const GridLevel lv = a.lv[l];
+        int3 c = grid_cell(g, inv_s, q.x, q.y, q.z);
+        int st = 0, cn = 0;
+        if (lane < 27) probe_cell(lv, a.tmask, c.x + dx, c.y + dy, c.z + dz, st, cn);
+        int total = cn;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-      if (total < k) continue;  // not enough points in the block: coarser level
-      topk_reset(t);
-      scan_lane_cells(t, k, lane, q, lv.sorted, st, cn);
-      const float r1 = s * 0.999f, r2 = 2.0f * s * 0.999f;
-      if (t.wd <= r1 * r1) { done = true; break; }
-      if (t.wd <= r2 * r2) {  // the 5x5x5 shell settles it
-        for (int base = 0; base < 125; base += 32) {
-          int o = base + lane;
-          int sx = o / 25 - 2, sy = (o / 5) % 5 - 2, sz = o % 5 - 2;
-          bool shell = o < 125 && (abs(sx) == 2 || abs(sy) == 2 || abs(sz) == 2);
-          int st2 = 0, cn2 = 0;
-          if (shell) probe_cell(lv, a.tmask, c.x + sx, c.y + sy, c.z + sz, st2, cn2);
-          scan_lane_cells(t, k, lane, q, lv.sorted, st2, cn2);
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        // A surface sampled at density rho puts ~9 rho s^2 points in the block and ~pi rho s^2 within distance s, so the block
+        // can only certify k neighbours when it holds >~ 2.9 k points: below 2.5 k go straight to the coarser level.
+        if (total < k || (2 * total < 5 * k && l + 1 < a.L)) continue;
+        if (total > kHeavyCandidates) {  // a lone warp is latency-bound: hand big blocks to the block-cooperative kernel
+          if (lane == 0) a.heavy_queue[atomicAdd(a.heavy_count, 1)] = make_int2(w, l);
+          deferred = true;
+          break;
         }
-        done = true;
-        break;
+        topk_reset(t);
+        scan_lane_cells<WIDE>(t, k, lane, q, lv.sorted, st, cn);
+        const float r1 = s * 0.999f;
+        if (t.wd <= r1 * r1) { done = true; break; }  // every point within s of q lies inside the 3x3x3 block
       }
     }
+    if (deferred) continue;
+    if (!done) {  // no level could certify the answer (tiny cloud, far outlier): whole cloud, block-cooperative
+      if (lane == 0) a.heavy_queue[atomicAdd(a.heavy_count, 1)] = make_int2(w, a.L);
+      continue;
+    }
+    int* row = a.nbr + (size_t)qi * k;
+    if (lane < k) row[lane] = t.i0;
+    if (WIDE && 32 + lane < k) row[32 + lane] = t.i1;
   }
-  if (!done) {  // whole cloud (level 0 copy, coalesced)
-    topk_reset(t);
-    scan_run(t, k, lane, q, a.lv[0].sorted, 0, a.n);
+}
+
+// Block-cooperative continuation for the deferred queries: the 8 warps of a block split the candidates of one query
+// (warp j takes batches j, j+8, ...), each keeps its own sorted top-k, warp 0 merges the eight lists through shared
+// memory and applies the same certificate; a query that still fails moves to the next level, and past the coarsest
+// level the block scans the whole cloud.
+template <bool WIDE>
+__global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid_heavy(GridArgs a) {
+  __shared__ float sd[kKnnGridWarps][64];
+  __shared__ int si[kKnnGridWarps][64];
+  __shared__ int s_next;
+  __shared__ int s_done;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int k = a.k;
+  GridGeom g = grid_geom(a.bbox_min, a.bbox_max);
+  int dx = 0, dy = 0, dz = 0;
+  if (lane < 27) {
+    int o = kBlockOrder[lane];
+    dx = o / 9 - 1; dy = (o / 3) % 3 - 1; dz = o % 3 - 1;
   }
-  int* row = a.nbr + (size_t)qi * k;
-  if (lane < k) row[lane] = t.i0;
-  if (32 + lane < k) row[32 + lane] = t.i1;
+  const int n_heavy = *a.heavy_count;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_next = atomicAdd(a.heavy_cursor, 1);
+    __syncthreads();
+    const int h = s_next;
+    if (h >= n_heavy) return;
+    const int2 item = a.heavy_queue[h];
+    float4 q = __ldg(&a.lv[0].sorted[item.x]);
+    const int qi = __float_as_int(q.w);
+    WarpTopK t;
+    for (int l = item.y; l <= a.L; l++) {
+      topk_reset(t);
+      float s = 0.f;
+      if (l < a.L) {
+        s = grid_cell_size(g, l, a.L);
+        const float inv_s = 1.0f / s;
+        const GridLevel lv = a.lv[l];
+        int3 c = grid_cell(g, inv_s, q.x, q.y, q.z);
+        int st = 0, cn = 0;
+        if (lane < 27) probe_cell(lv, a.tmask, c.x + dx, c.y + dy, c.z + dz, st, cn);
+        int total = cn;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        if (total < k) continue;  // warp-uniform and identical in all warps
+        scan_lane_cells_strided<WIDE>(t, k, lane, q, lv.sorted, st, cn, wid, kKnnGridWarps);
+      } else {
+        scan_run_strided<WIDE>(t, k, lane, q, a.lv[0].sorted, 0, a.n, wid, kKnnGridWarps);
+      }
+      // merge the per-warp lists in warp 0
+      sd[wid][lane] = t.d0; si[wid][lane] = t.i0;
+      sd[wid][32 + lane] = t.d1; si[wid][32 + lane] = t.i1;
+      __syncthreads();
+      if (wid == 0) {
+        for (int ww = 1; ww < kKnnGridWarps; ww++) {
+          topk_offer<WIDE>(t, k, lane, lane < k, sd[ww][lane], si[ww][lane]);
+          if (WIDE) topk_offer<WIDE>(t, k, lane, 32 + lane < k, sd[ww][32 + lane], si[ww][32 + lane]);
+        }
+        const float r1 = s * 0.999f;
+        const bool ok = (l == a.L) || (t.wd <= r1 * r1);
+        if (ok) {
+          int* row = a.nbr + (size_t)qi * k;
+          if (lane < k) row[lane] = t.i0;
+          if (WIDE && 32 + lane < k) row[32 + lane] = t.i1;
+        }
+        if (lane == 0) s_done = ok ? 1 : 0;
+      }
+      __syncthreads();
+      if (s_done) break;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -618,7 +869,7 @@ size_t knn_grid_scratch_bytes(int n, int* levels_out, unsigned* table_size_out) 
   if (levels_out) *levels_out = L;
   if (table_size_out) *table_size_out = T;
   size_t per_level = (size_t)T * (8 + 4 + 4 + 4) + (size_t)n * (16 + 4);
-  return 4096 + (size_t)L * per_level;
+  return 4096 + (size_t)L * per_level + (size_t)n * 8;
 }
 
 // scratch layout:  [0xFF-filled : bbox min (16 B) | keys of all levels]
@@ -639,6 +890,9 @@ cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned 
   unsigned char* z_begin = p;
   a.bbox_max = reinterpret_cast<unsigned*>(p); p += 16;
   a.level_cursor = reinterpret_cast<int*>(p); p += 64;
+  a.query_cursor = a.level_cursor + 15;
+  a.heavy_count = a.level_cursor + 14;
+  a.heavy_cursor = a.level_cursor + 13;
   for (int l = 0; l < L; l++) {
     a.lv[l].cnt = reinterpret_cast<int*>(p); p += (size_t)T * 4;
     a.lv[l].fill = reinterpret_cast<int*>(p); p += (size_t)T * 4;
@@ -647,6 +901,8 @@ cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned 
   for (int l = 0; l < L; l++) { a.lv[l].start = reinterpret_cast<int*>(p); p += (size_t)T * 4; }
   for (int l = 0; l < L; l++) { a.lv[l].sorted = reinterpret_cast<float4*>(p); p += (size_t)n * 16; }
   for (int l = 0; l < L; l++) { a.lv[l].pslot = reinterpret_cast<int*>(p); p += (size_t)n * 4; }
+  p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
+  a.heavy_queue = reinterpret_cast<int2*>(p); p += (size_t)n * 8;
   cudaError_t e;
   if ((e = cudaMemsetAsync(ff_begin, 0xFF, ff_bytes, stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(z_begin, 0, z_bytes, stream)) != cudaSuccess) return e;
@@ -655,8 +911,17 @@ cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned 
   k_grid_count<<<dim3(nb, L), 256, 0, stream>>>(a);
   k_grid_alloc<<<dim3((T + 255) / 256, L), 256, 0, stream>>>(a);
   k_grid_scatter<<<dim3(nb, L), 256, 0, stream>>>(a);
-  k_knn_grid<<<(n + kKnnGridWarps - 1) / kKnnGridWarps, kKnnGridWarps * 32, 0, stream>>>(a, force_bruteforce);
-  if (launches) *launches = 5;
+  int qblocks = (n + kKnnGridWarps - 1) / kKnnGridWarps;
+  if (qblocks > 148 * 8) qblocks = 148 * 8;  // persistent: 8 blocks x 8 warps per SM, queries pulled from a counter
+  int hblocks = qblocks < 148 * 4 ? qblocks : 148 * 4;
+  if (k <= 32) {
+    k_knn_grid<false><<<qblocks, kKnnGridWarps * 32, 0, stream>>>(a, force_bruteforce);
+    k_knn_grid_heavy<false><<<hblocks, kKnnGridWarps * 32, 0, stream>>>(a);
+  } else {
+    k_knn_grid<true><<<qblocks, kKnnGridWarps * 32, 0, stream>>>(a, force_bruteforce);
+    k_knn_grid_heavy<true><<<hblocks, kKnnGridWarps * 32, 0, stream>>>(a);
+  }
+  if (launches) *launches = 6;
   return cudaGetLastError();
 }
 
