@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "vgicp_lsq_default_params", "vgicp_align", "vgicp_transform_source",
     "vgicp_get_launch_count", "vgicp_synchronize", "vgicp_get_stream",
     "vgicp_set_source_cloud_device", "vgicp_set_target_cloud_device", "vgicp_set_profiling", "vgicp_get_profile", "vgicp_profile_category_name",
-    "vgicp_set_knn_mode",
+    "vgicp_set_knn_mode", "vgicp_register",
 ]
 PROF_NUM_CATEGORIES = 7
 
@@ -124,6 +124,7 @@ def load_library():
         "vgicp_set_target_cloud_device": [hp, C.c_void_p, C.c_size_t, C.c_size_t],
         "vgicp_set_profiling": [hp, C.c_int],
         "vgicp_set_knn_mode": [hp, C.c_int],
+        "vgicp_register": [hp, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, dp, C.POINTER(LsqParams), C.POINTER(AlignResult)],
         "vgicp_get_profile": [hp, dp, C.POINTER(C.c_uint64), C.c_int],
     }
     for name, argtypes in sig.items():
@@ -383,6 +384,19 @@ class Core:
         res = AlignResult()
         self._check(self._lib.vgicp_align(self._h, _dp(g), C.byref(params), C.byref(res)))
         return res
+
+    def register_raw(self, tgt_ptr, n_t, src_ptr, n_s, stride=12, on_device=False, k=20, reg=REG_PLANE, guess=None, params=None):
+        """clear + setInputTarget + setInputSource + align in one C call (pointers: host, or device when on_device)."""
+        res = AlignResult()
+        g = None if guess is None else _dp(pose_to_c(guess))
+        self._check(self._lib.vgicp_register(self._h, tgt_ptr, n_t, src_ptr, n_s, stride, int(on_device), int(k), int(reg), g, C.byref(params) if params is not None else None, C.byref(res)))
+        return res
+
+    def register(self, target, source, k=20, reg=REG_PLANE, guess=None, params=None):
+        t, nt, st = self._cloud(target)
+        s_, ns, ss = self._cloud(source)
+        assert st == ss
+        return self.register_raw(t.ctypes.data, nt, s_.ctypes.data, ns, st, False, k, reg, guess, params)
 
     def transform_source(self, T, stride=12, out=None):
         n = self.num_source_points()

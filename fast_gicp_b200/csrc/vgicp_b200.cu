@@ -859,6 +859,25 @@ int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* 
   return VGICP_OK;
 }
 
+// clear + setInputTarget + setInputSource + align in one call (the body of the reference's benchmark loop, src/align.cpp:72-81)
+int vgicp_register(vgicp_handle h, const float* target_xyz, size_t n_target, const float* source_xyz, size_t n_source, size_t stride_bytes, int on_device, int k,
+                   int regularization_method, const double guess[16], const vgicp_lsq_params* params, vgicp_align_result* result) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  int rc;
+  h->target.k = 0; h->target.has_cov = false; h->map.built = false;
+  if ((rc = set_cloud(h, h->target, target_xyz, n_target, stride_bytes, on_device != 0))) return rc;
+  if ((rc = find_neighbors(h, h->target, k))) return rc;
+  if ((rc = calc_covariances(h, h->target, regularization_method))) return rc;
+  if ((rc = build_voxelmap(h))) return rc;
+  h->source.k = 0; h->source.has_cov = false;
+  if ((rc = set_cloud(h, h->source, source_xyz, n_source, stride_bytes, on_device != 0))) return rc;
+  if ((rc = find_neighbors(h, h->source, k))) return rc;
+  if ((rc = calc_covariances(h, h->source, regularization_method))) return rc;
+  double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  return vgicp_align(h, guess ? guess : I, params, result);
+}
+
 int vgicp_transform_source(vgicp_handle h, const double T[16], float* out_xyz, size_t cap, size_t stride) {
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);

@@ -477,98 +477,88 @@ __global__ void k_grid_scatter(GridArgs a) {
   lv.sorted[base + rank] = p;
 }
 
-// ---- warp-level sorted top-k (k <= 64): rank r lives in lane r & 31, register r >> 5.  WIDE=false (k <= 32) keeps a
-// single register set: an insertion is 2 broadcasts + 1 ballot + 2 shuffle-ups + 2 broadcasts. ----
+// ---- warp-level sorted top-k (k <= 64): rank r lives in lane r & 31, register r >> 5.
+// An entry is one 64-bit key: (bits of d2) << 32 | index.  d2 >= 0, so unsigned order of the key == ascending (d2, index).
+// WIDE=false (k <= 32) keeps a single register set. ----
+typedef unsigned long long tkey;
+constexpr tkey kKeyInf = 0x7f8000007fffffffULL;  // (+inf, INT_MAX)
+__device__ __forceinline__ tkey make_key(float d, int i) { return ((tkey)__float_as_uint(d) << 32) | (unsigned)i; }
+
 struct WarpTopK {
-  float d0, d1;
-  int i0, i1;
-  float wd;  // current worst (rank k-1), broadcast
-  int wi;
+  tkey e0, e1;
+  tkey worst;  // entry of rank k-1, broadcast
 };
-__device__ __forceinline__ bool pair_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
 
-__device__ __forceinline__ void topk_reset(WarpTopK& t) {
-  t.d0 = t.d1 = __int_as_float(0x7f800000);
-  t.i0 = t.i1 = 0x7fffffff;
-  t.wd = __int_as_float(0x7f800000);
-  t.wi = 0x7fffffff;
-}
+__device__ __forceinline__ void topk_reset(WarpTopK& t) { t.e0 = t.e1 = t.worst = kKeyInf; }
 
-// compare-exchange step of a bitonic network over the 32 lanes: lane keeps the smaller pair when keep_min
-__device__ __forceinline__ void cmpx(float& d, int& i, int stride, bool keep_min) {
-  float od = __shfl_xor_sync(0xffffffffu, d, stride);
-  int oi = __shfl_xor_sync(0xffffffffu, i, stride);
-  bool o_less = pair_less(od, oi, d, i);
-  bool swap = keep_min ? o_less : pair_less(d, i, od, oi);
-  if (swap) { d = od; i = oi; }
+// compare-exchange step of a bitonic network over the 32 lanes: lane keeps the smaller key when keep_min
+__device__ __forceinline__ void cmpx(tkey& e, int stride, bool keep_min) {
+  tkey o = __shfl_xor_sync(0xffffffffu, e, stride);
+  if ((o < e) == keep_min) e = o;  // keys are distinct except (inf, INT_MAX) padding, where either choice is the same
 }
 
 // Merge a batch of 32 candidates into the sorted list (k <= 32): bitonic-sort the batch (15 steps), take the element-wise
-// minimum with the reversed list (the 32 smallest of the 64, a bitonic sequence), bitonic-merge (5 steps).  ~170
-// instructions however many candidates make it into the list, against ~35 per single insertion.
-__device__ __forceinline__ void topk_merge32(WarpTopK& t, int k, int lane, float cd, int ci) {
+// minimum with the reversed list (the 32 smallest of the 64, a bitonic sequence), bitonic-merge (5 steps).
+__device__ __forceinline__ void topk_merge32(WarpTopK& t, int k, int lane, tkey c) {
 #pragma unroll
   for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       bool up = (lane & size) == 0 || size == 32;
       bool lower = (lane & stride) == 0;
-      cmpx(cd, ci, stride, lower == up);
+      cmpx(c, stride, lower == up);
     }
   }
-  float rd = __shfl_sync(0xffffffffu, cd, 31 - lane);
-  int ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
-  if (pair_less(rd, ri, t.d0, t.i0)) { t.d0 = rd; t.i0 = ri; }
+  if (t.e0 == kKeyInf && __all_sync(0xffffffffu, t.e0 == kKeyInf)) {
+    t.e0 = c;  // empty list: the sorted batch is the list
+  } else {
+    tkey r = __shfl_sync(0xffffffffu, c, 31 - lane);
+    if (r < t.e0) t.e0 = r;
 #pragma unroll
-  for (int stride = 16; stride > 0; stride >>= 1) cmpx(t.d0, t.i0, stride, (lane & stride) == 0);
-  t.wd = __shfl_sync(0xffffffffu, t.d0, k - 1);
-  t.wi = __shfl_sync(0xffffffffu, t.i0, k - 1);
+    for (int stride = 16; stride > 0; stride >>= 1) cmpx(t.e0, stride, (lane & stride) == 0);
+  }
+  t.worst = __shfl_sync(0xffffffffu, t.e0, k - 1);
 }
 
 // all 32 lanes call this with their candidate (valid=false for padding lanes)
 template <bool WIDE>
 __device__ __forceinline__ void topk_offer(WarpTopK& t, int k, int lane, bool valid, float cd, int ci) {
-  const bool pass = valid && pair_less(cd, ci, t.wd, t.wi);
+  const tkey c = make_key(cd, ci);
+  const bool pass = valid && c < t.worst;
   unsigned m = __ballot_sync(0xffffffffu, pass);
-  if (!WIDE && __popc(m) > 4) {  // many entrants: one sort-merge instead of one insertion each
-    topk_merge32(t, k, lane, pass ? cd : __int_as_float(0x7f800000), pass ? ci : 0x7fffffff);
+  if (!WIDE && __popc(m) > 3) {  // many entrants: one sort-merge instead of one insertion each
+    topk_merge32(t, k, lane, pass ? c : kKeyInf);
     return;
   }
   while (m) {
     int src = __ffs(m) - 1;
     m &= m - 1;
-    float nd = __shfl_sync(0xffffffffu, cd, src);
-    int ni = __shfl_sync(0xffffffffu, ci, src);
-    if (!pair_less(nd, ni, t.wd, t.wi)) continue;  // worst moved since the ballot (warp-uniform branch)
-    unsigned b0 = __ballot_sync(0xffffffffu, pair_less(t.d0, t.i0, nd, ni));
-    int p = __popc(b0);  // rank of the new entry
-    float up_d0 = __shfl_up_sync(0xffffffffu, t.d0, 1);
-    int up_i0 = __shfl_up_sync(0xffffffffu, t.i0, 1);
+    tkey n = __shfl_sync(0xffffffffu, c, src);
+    if (!(n < t.worst)) continue;  // worst moved since the ballot (warp-uniform branch)
+    int p = __popc(__ballot_sync(0xffffffffu, t.e0 < n));  // rank of the new entry
+    tkey up0 = __shfl_up_sync(0xffffffffu, t.e0, 1);
     const int kr = k - 1;
     if (WIDE) {
-      unsigned b1 = __ballot_sync(0xffffffffu, pair_less(t.d1, t.i1, nd, ni));
-      p += __popc(b1);
-      float up_d1 = __shfl_up_sync(0xffffffffu, t.d1, 1);
-      int up_i1 = __shfl_up_sync(0xffffffffu, t.i1, 1);
-      float carry_d = __shfl_sync(0xffffffffu, t.d0, 31);  // rank 31 -> 32 crosses registers
-      int carry_i = __shfl_sync(0xffffffffu, t.i0, 31);
+      p += __popc(__ballot_sync(0xffffffffu, t.e1 < n));
+      tkey up1 = __shfl_up_sync(0xffffffffu, t.e1, 1);
+      tkey carry = __shfl_sync(0xffffffffu, t.e0, 31);  // rank 31 -> 32 crosses registers
       int r1 = 32 + lane;
-      if (r1 > p) { t.d1 = (lane == 0) ? carry_d : up_d1; t.i1 = (lane == 0) ? carry_i : up_i1; }
-      else if (r1 == p) { t.d1 = nd; t.i1 = ni; }
+      if (r1 > p) t.e1 = (lane == 0) ? carry : up1;
+      else if (r1 == p) t.e1 = n;
     }
-    if (lane > p) { t.d0 = up_d0; t.i0 = up_i0; }
-    else if (lane == p) { t.d0 = nd; t.i0 = ni; }
+    if (lane > p) t.e0 = up0;
+    else if (lane == p) t.e0 = n;
     if (WIDE) {
-      float w0 = __shfl_sync(0xffffffffu, t.d0, kr & 31), w1 = __shfl_sync(0xffffffffu, t.d1, kr & 31);
-      int x0 = __shfl_sync(0xffffffffu, t.i0, kr & 31), x1 = __shfl_sync(0xffffffffu, t.i1, kr & 31);
-      t.wd = (kr < 32) ? w0 : w1;
-      t.wi = (kr < 32) ? x0 : x1;
+      tkey w0 = __shfl_sync(0xffffffffu, t.e0, kr & 31), w1 = __shfl_sync(0xffffffffu, t.e1, kr & 31);
+      t.worst = (kr < 32) ? w0 : w1;
     } else {
-      t.wd = __shfl_sync(0xffffffffu, t.d0, kr);
-      t.wi = __shfl_sync(0xffffffffu, t.i0, kr);
+      t.worst = __shfl_sync(0xffffffffu, t.e0, kr);
     }
   }
 }
+
+__device__ __forceinline__ float topk_worst_d2(const WarpTopK& t) { return __uint_as_float((unsigned)(t.worst >> 32)); }
+__device__ __forceinline__ int key_index(tkey e) { return (int)(unsigned)(e & 0xffffffffULL); }
 
 __device__ __forceinline__ float knn_d2(float4 q, float4 t) {  // (dx*dx + dy*dy) + dz*dz, no contraction
   float dx = __fsub_rn(t.x, q.x), dy = __fsub_rn(t.y, q.y), dz = __fsub_rn(t.z, q.z);
@@ -759,7 +749,7 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid(GridArgs a, int
         topk_reset(t);
         scan_lane_cells<WIDE>(t, k, lane, q, lv.sorted, st, cn);
         const float r1 = s * 0.999f;
-        if (t.wd <= r1 * r1) { done = true; break; }  // every point within s of q lies inside the 3x3x3 block
+        if (topk_worst_d2(t) <= r1 * r1) { done = true; break; }  // every point within s of q lies inside the 3x3x3 block
       }
     }
     if (deferred) continue;
@@ -768,8 +758,8 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid(GridArgs a, int
       continue;
     }
     int* row = a.nbr + (size_t)qi * k;
-    if (lane < k) row[lane] = t.i0;
-    if (WIDE && 32 + lane < k) row[32 + lane] = t.i1;
+    if (lane < k) row[lane] = key_index(t.e0);
+    if (WIDE && 32 + lane < k) row[32 + lane] = key_index(t.e1);
   }
 }
 
@@ -779,8 +769,7 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid(GridArgs a, int
 // level the block scans the whole cloud.
 template <bool WIDE>
 __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid_heavy(GridArgs a) {
-  __shared__ float sd[kKnnGridWarps][64];
-  __shared__ int si[kKnnGridWarps][64];
+  __shared__ tkey se[kKnnGridWarps][64];
   __shared__ int s_next;
   __shared__ int s_done;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -821,20 +810,24 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid_heavy(GridArgs 
         scan_run_strided<WIDE>(t, k, lane, q, a.lv[0].sorted, 0, a.n, wid, kKnnGridWarps);
       }
       // merge the per-warp lists in warp 0
-      sd[wid][lane] = t.d0; si[wid][lane] = t.i0;
-      sd[wid][32 + lane] = t.d1; si[wid][32 + lane] = t.i1;
+      se[wid][lane] = t.e0;
+      se[wid][32 + lane] = t.e1;
       __syncthreads();
       if (wid == 0) {
         for (int ww = 1; ww < kKnnGridWarps; ww++) {
-          topk_offer<WIDE>(t, k, lane, lane < k, sd[ww][lane], si[ww][lane]);
-          if (WIDE) topk_offer<WIDE>(t, k, lane, 32 + lane < k, sd[ww][32 + lane], si[ww][32 + lane]);
+          tkey e = se[ww][lane];
+          topk_offer<WIDE>(t, k, lane, lane < k, __uint_as_float((unsigned)(e >> 32)), key_index(e));
+          if (WIDE) {
+            e = se[ww][32 + lane];
+            topk_offer<WIDE>(t, k, lane, 32 + lane < k, __uint_as_float((unsigned)(e >> 32)), key_index(e));
+          }
         }
         const float r1 = s * 0.999f;
-        const bool ok = (l == a.L) || (t.wd <= r1 * r1);
+        const bool ok = (l == a.L) || (topk_worst_d2(t) <= r1 * r1);
         if (ok) {
           int* row = a.nbr + (size_t)qi * k;
-          if (lane < k) row[lane] = t.i0;
-          if (WIDE && 32 + lane < k) row[32 + lane] = t.i1;
+          if (lane < k) row[lane] = key_index(t.e0);
+          if (WIDE && 32 + lane < k) row[32 + lane] = key_index(t.e1);
         }
         if (lane == 0) s_done = ok ? 1 : 0;
       }

@@ -146,6 +146,10 @@ VGICP_API void vgicp_lsq_default_params(vgicp_lsq_params* p);
 /* Whole LsqRegistration::computeTransformation loop (lsq_registration_impl.hpp:53-79,106-168) run device-resident:
  * same linearize / compute_error evaluations, same LM logic in double, no host round trip per evaluation. */
 VGICP_API int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* params, vgicp_align_result* result);
+/* One whole registration: clearTarget/clearSource + setInputTarget + setInputSource + align (the body of the reference's
+ * benchmark loop, src/align.cpp:72-81) with GPU k-NN covariances.  xyz are host pointers, or device pointers when on_device != 0. */
+VGICP_API int vgicp_register(vgicp_handle h, const float* target_xyz, size_t n_target, const float* source_xyz, size_t n_source, size_t stride_bytes, int on_device, int k,
+                             int regularization_method, const double guess[16], const vgicp_lsq_params* params, vgicp_align_result* result);
 /* pcl::transformPointCloud of the source by T (lsq_registration_impl.hpp:78) on the device; out: n x stride floats */
 VGICP_API int vgicp_transform_source(vgicp_handle h, const double T[16], float* out_xyz, size_t capacity_points, size_t stride_bytes);
 /* set_{source,target}_cloud with the points already resident in this GPU's memory (device pointer, same layout rules);
