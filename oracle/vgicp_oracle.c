@@ -1117,19 +1117,32 @@ typedef struct {
 } F64Problem;
 
 static void f64_update_correspondences(F64Problem* p, const double* T) { /* fast_vgicp_impl.hpp:73-116 */
-  long cnt = 0;
-  /* serial gather keeps the list deterministic; the reference concatenates per-thread lists */
+  /* parallel lookup like the reference (:82-97: per-thread lists, concatenated); two passes keep the list in point
+   * order whatever the thread count */
+  int* per_point = (int*)malloc(sizeof(int) * (size_t)(p->n_src + 1));
+  int* found = (int*)malloc(sizeof(int) * (size_t)(p->n_src > 0 ? p->n_src : 1) * (size_t)p->n_off);
+#pragma omp parallel for num_threads(p->num_threads) schedule(guided, 8)
   for (int i = 0; i < p->n_src; i++) {
     double a[3] = {p->src[3 * (size_t)i], p->src[3 * (size_t)i + 1], p->src[3 * (size_t)i + 2]}, q[3];
     for (int r = 0; r < 3; r++) q[r] = T[r] * a[0] + T[4 + r] * a[1] + T[8 + r] * a[2] + T[12 + r];
     int c[3];
     coord64(q, p->res, c);
+    int m = 0;
     for (int o = 0; o < p->n_off; o++) {
       int cc[3] = {c[0] + p->offsets[3 * o], c[1] + p->offsets[3 * o + 1], c[2] + p->offsets[3 * o + 2]};
       int v = map64_find(p->map, cc, 0, NULL);
-      if (v >= 0) { p->corr[2 * cnt] = i; p->corr[2 * cnt + 1] = v; cnt++; }
+      if (v >= 0) found[(size_t)i * p->n_off + m++] = v;
     }
+    per_point[i] = m;
   }
+  long cnt = 0;
+  for (int i = 0; i < p->n_src; i++) { int m = per_point[i]; per_point[i] = (int)cnt; cnt += m; }
+  per_point[p->n_src] = (int)cnt;
+#pragma omp parallel for num_threads(p->num_threads) schedule(static)
+  for (int i = 0; i < p->n_src; i++)
+    for (int j = per_point[i]; j < per_point[i + 1]; j++) { p->corr[2 * (size_t)j] = i; p->corr[2 * (size_t)j + 1] = found[(size_t)i * p->n_off + (j - per_point[i])]; }
+  free(per_point);
+  free(found);
   p->n_corr = cnt;
   double R[9], Rt[9];
   for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) { M3(R, r, c) = T[c * 4 + r]; M3(Rt, c, r) = T[c * 4 + r]; }
