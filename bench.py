@@ -202,23 +202,20 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
 
     from fast_gicp_b200 import FastVGICPCuda
+    from fast_gicp_b200 import distributed as D
     from fast_gicp_b200.core import REG_PLANE, Core, pose_from_c
 
+    D.init("nccl", dev)  # one rank per GPU; used for the barrier and the max-over-ranks of the device time only
+
     def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        D.barrier(cuda=True)
 
     tgt, src = w["target"], w["source"]
     n_t, n_s = len(tgt), len(src)
@@ -368,10 +365,7 @@ def main():
 
     note("single-stream pass done")
     # ---- max over ranks
-    if world > 1:
-        t = torch.tensor([total_ms, total_ms_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, total_ms_e2e = float(t[0]), float(t[1])
+    total_ms, total_ms_e2e = D.max_over_ranks([total_ms, total_ms_e2e], device=dev)
 
     # ---- per-kernel profile (separate pass, events around every launch) -> roofline of the dominant kernel
     core.set_profiling(True)
@@ -385,8 +379,7 @@ def main():
     per_kernel = {k: {"ms_per_step": v[0] / n_prof, "launches_per_step": v[1] / n_prof} for k, v in prof.items() if v[1]}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        D.finalize()
         return
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -452,8 +445,7 @@ def main():
         "pose_check": {"translation": [float(x) for x in T_val[:3, 3]], "e2e_vs_resident_max_abs": float(np.abs(np.asarray(T_e2e, dtype=np.float64) - T_val).max())},
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    D.finalize()
 
 
 if __name__ == "__main__":

@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "vgicp_lsq_default_params", "vgicp_align", "vgicp_transform_source",
     "vgicp_get_launch_count", "vgicp_synchronize", "vgicp_get_stream",
     "vgicp_set_source_cloud_device", "vgicp_set_target_cloud_device", "vgicp_set_profiling", "vgicp_get_profile", "vgicp_profile_category_name",
-    "vgicp_set_knn_mode", "vgicp_register",
+    "vgicp_set_knn_mode", "vgicp_register", "vgicp_set_align_mode",
 ]
 PROF_NUM_CATEGORIES = 7
 
@@ -124,6 +124,7 @@ def load_library():
         "vgicp_set_target_cloud_device": [hp, C.c_void_p, C.c_size_t, C.c_size_t],
         "vgicp_set_profiling": [hp, C.c_int],
         "vgicp_set_knn_mode": [hp, C.c_int],
+        "vgicp_set_align_mode": [hp, C.c_int],
         "vgicp_register": [hp, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, dp, C.POINTER(LsqParams), C.POINTER(AlignResult)],
         "vgicp_get_profile": [hp, dp, C.POINTER(C.c_uint64), C.c_int],
     }
@@ -227,6 +228,9 @@ class Core:
         """Points already resident in this GPU's memory (e.g. a torch CUDA tensor's data_ptr())."""
         fn = self._lib.vgicp_set_source_cloud_device if which == "source" else self._lib.vgicp_set_target_cloud_device
         self._check(fn(self._h, dev_ptr, n, stride))
+
+    def set_align_mode(self, mode):
+        self._check(self._lib.vgicp_set_align_mode(self._h, int(mode)))
 
     def set_knn_mode(self, mode):
         self._check(self._lib.vgicp_set_knn_mode(self._h, int(mode)))

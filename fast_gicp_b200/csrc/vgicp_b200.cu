@@ -96,6 +96,9 @@ struct vgicp_context {
 
   DevBuf<unsigned char> staging;
   DevBuf<unsigned char> knn_scratch;
+  int align_mode = 1;  // 1 = host-driven loop over the evaluation kernels (default: faster today), 0 = device-resident LM chain
+  LmState* d_lm = nullptr;
+  LmState* h_lm = nullptr;  // pinned
   int knn_mode = 0;  // 0 = hash grid (default), 1 = warp-cooperative scan of the whole cloud, 2 = legacy per-thread scan
   DevBuf<double> partials;
   DevBuf<int> corr_ids;
@@ -347,24 +350,39 @@ int build_voxelmap(vgicp_handle h) {
   return VGICP_OK;
 }
 
-// one evaluation: launches the fused lookup+derivative kernel; result lands in h->h_out after the stream sync
-int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H) {
+// arguments + launch geometry of an evaluation kernel
+struct LinLaunch {
+  LinArgs a;
+  int grid;
+  int G;
+};
+LinLaunch make_lin_launch(vgicp_handle h) {
   Cloud& s = h->source;
   VoxelMap& m = h->map;
-  LinArgs a;
+  LinLaunch L;
+  LinArgs& a = L.a;
   a.pts = s.pts.p; a.covA = s.covA.p; a.covB = s.covB.p; a.n = s.n;
   a.buckets = m.buckets.p; a.mask = (unsigned)(m.num_buckets - 1); a.max_scan = m.max_scan; a.vox = m.vox.p;
   a.offsets = h->d_offsets.p; a.n_off = (int)h->h_offsets.size(); a.res = m.res;
-  a.Tlin = h->lin; a.Teval = Teval;
+  a.Tlin = h->lin; a.Teval = h->lin;
   a.partials = h->partials.p; a.ticket = h->d_ticket; a.out = h->d_out;
   // lanes per source point: split the neighbour cells of a point over G lanes while the cloud is too small to fill the
   // GPU with one thread per point (latency-bound regime); one lane per point once it is large (ALU/bandwidth-bound regime)
-  const int n_off = (int)h->h_offsets.size();
+  const int n_off = a.n_off;
   const bool wide = s.n < 400000 && n_off > 1;
-  const int G = !wide ? 1 : (n_off <= 7 ? 4 : 8);
-  long long tasks = (long long)(s.n > 0 ? s.n : 1) * G;
-  int grid = (int)((tasks + kLinThreads - 1) / kLinThreads);
-  if (grid > kLinMaxBlocks) grid = kLinMaxBlocks;
+  L.G = !wide ? 1 : (n_off <= 7 ? 4 : 8);
+  long long tasks = (long long)(s.n > 0 ? s.n : 1) * L.G;
+  long long grid = (tasks + kLinThreads - 1) / kLinThreads;
+  L.grid = (int)(grid > kLinMaxBlocks ? kLinMaxBlocks : grid);
+  return L;
+}
+
+// one evaluation: launches the fused lookup+derivative kernel; result lands in h->h_out after the stream sync
+int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H) {
+  LinLaunch L = make_lin_launch(h);
+  LinArgs& a = L.a;
+  a.Teval = Teval;
+  const int grid = L.grid, G = L.G;
 #define LAUNCH_LIN_G(MODE, GG)                                                           \
   do {                                                                                   \
     if (want_H) k_linearize<MODE, true, GG><<<grid, kLinThreads, 0, h->stream>>>(a);     \
@@ -385,6 +403,32 @@ int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H) {
   }
 #undef LAUNCH_LIN_G
 #undef LAUNCH_LIN
+  prof_end(h);
+  h->launches++;
+  CU_TRY(h, cudaGetLastError());
+  return VGICP_OK;
+}
+
+// one link of the device-resident optimiser chain
+int launch_lm_step(vgicp_handle h, const LinLaunch& L) {
+  const LinArgs& a = L.a;
+  const int grid = L.grid, G = L.G;
+#define LAUNCH_LM_G(MODE, GG) k_lm_step<MODE, GG><<<grid, kLinThreads, 0, h->stream>>>(a, h->d_lm)
+#define LAUNCH_LM(MODE)                 \
+  do {                                  \
+    if (G == 8) LAUNCH_LM_G(MODE, 8);   \
+    else if (G == 4) LAUNCH_LM_G(MODE, 4); \
+    else LAUNCH_LM_G(MODE, 1);          \
+  } while (0)
+  prof_begin(h, VGICP_PROF_LINEARIZE);
+  switch (h->offset_mode) {
+    case 1: LAUNCH_LM_G(1, 1); break;
+    case 7: LAUNCH_LM(7); break;
+    case 27: LAUNCH_LM(27); break;
+    default: LAUNCH_LM(0); break;
+  }
+#undef LAUNCH_LM_G
+#undef LAUNCH_LM
   prof_end(h);
   h->launches++;
   CU_TRY(h, cudaGetLastError());
@@ -442,6 +486,8 @@ int vgicp_create(int device, vgicp_handle* out) {
   ok = ok && cudaMalloc(&h->d_out, 64 * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMallocHost(&h->h_out, 64 * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMallocHost(&h->h_counters, 4 * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc(&h->d_lm, sizeof(LmState)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&h->h_lm, sizeof(LmState)) == cudaSuccess;
   ok = ok && h->partials.reserve((size_t)kLinMaxBlocks * kLinValues) == cudaSuccess;
   ok = ok && cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
@@ -472,6 +518,8 @@ int vgicp_destroy(vgicp_handle h) {
   if (h->d_out) cudaFree(h->d_out);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_counters) cudaFreeHost(h->h_counters);
+  if (h->d_lm) cudaFree(h->d_lm);
+  if (h->h_lm) cudaFreeHost(h->h_lm);
   for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->prof_pool) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -793,6 +841,48 @@ int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* 
   if (!h->source.has_pts || !h->source.has_cov) return fail(h, VGICP_ERR_BAD_STATE, "align: source points and covariances required");
   if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "align: target voxel map not built");
 
+  if (h->align_mode == 0) {
+    // device-resident loop: initialise the state block, enqueue evaluation links, read the state back once per chunk
+    LmState* st = h->h_lm;
+    memset(st, 0, sizeof(LmState));
+    memcpy(st->x0, guess, sizeof(st->x0));
+    for (int i = 0; i < 6; i++) st->final_H[i * 7] = 1.0;  // final_hessian_.setIdentity()
+    st->lambda = -1.0;
+    st->nu = 2.0;
+    st->rotation_epsilon = P.rotation_epsilon;
+    st->transformation_epsilon = P.transformation_epsilon;
+    st->lm_init_lambda_factor = P.lm_init_lambda_factor;
+    st->max_iterations = P.max_iterations;
+    st->lm_max_iterations = P.lm_max_iterations;
+    st->use_gauss_newton = P.use_gauss_newton;
+    st->phase = P.max_iterations > 0 ? kLmLinearize : kLmDone;
+    st->lin_pose = to_pose(guess);
+    st->eval_pose = st->lin_pose;
+    CU_TRY(h, cudaMemcpyAsync(h->d_lm, st, sizeof(LmState), cudaMemcpyHostToDevice, h->stream));
+    const LinLaunch L = make_lin_launch(h);
+    const int chunk = 12;  // a typical registration needs ~10 evaluations; finished chains return immediately
+    for (int guard = 0; guard < 4096; guard++) {
+      for (int c = 0; c < chunk; c++) {
+        int rc = launch_lm_step(h, L);
+        if (rc) return rc;
+      }
+      CU_TRY(h, cudaMemcpyAsync(st, h->d_lm, sizeof(LmState), cudaMemcpyDeviceToHost, h->stream));
+      CU_TRY(h, cudaStreamSynchronize(h->stream));
+      if (st->phase == kLmDone) break;
+    }
+    memset(res, 0, sizeof(*res));
+    memcpy(res->T, st->x0, sizeof(res->T));
+    memcpy(res->H, st->final_H, sizeof(res->H));
+    res->nr_iterations = st->nr_iterations;
+    res->converged = st->converged;
+    res->n_linearize = st->n_linearize;
+    res->n_compute_error = st->n_error;
+    res->lm_failed = st->lm_failed;
+    h->lin = st->lin_pose;  // linearized_x of the last linearisation
+    h->has_lin = true;
+    return VGICP_OK;
+  }
+
   Iso3d x0;
   memcpy(x0.m, guess, sizeof(x0.m));
   double lambda = -1.0;
@@ -911,6 +1001,13 @@ int vgicp_set_target_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, 
   h->target.has_cov = false;
   h->map.built = false;
   return set_cloud(h, h->target, d_xyz, n, stride_bytes, true);
+}
+
+int vgicp_set_align_mode(vgicp_handle h, int mode) {
+  CHECK_HANDLE(h);
+  if (mode < 0 || mode > 1) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_align_mode: 0 device-resident loop, 1 host-driven loop");
+  h->align_mode = mode;
+  return VGICP_OK;
 }
 
 int vgicp_set_knn_mode(vgicp_handle h, int mode) {

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "lsq_math.hpp"
 #include "vgicp_stage1.cuh"
 
 namespace vgicp {
@@ -329,16 +330,14 @@ __device__ __forceinline__ int3 fixed_offset(int o) {
 // G lanes share one source point and split its neighbour cells (lane s takes offsets s, s+G, ...): at 17k points a
 // one-thread-per-point mapping leaves one warp per scheduler and 27 serial dependent probes per thread; with G = 8 the
 // probes of a lane (<= 4) are issued together and the grid has 8x the warps to hide the L2 latency.
+// per-thread accumulation of the NV sums over this thread's (point, lane) tasks
 template <int MODE, bool WANT_H, int G>
-__global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
+__device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl, const Pose& Te, float* sum) {
   constexpr int NV = WANT_H ? kLinValues : 1;
   constexpr int NOFF = MODE == 0 ? 0 : MODE;
   constexpr int CELLS = MODE == 0 ? 4 : ((NOFF + G - 1) / G < 4 ? (NOFF + G - 1) / G : 4);  // cells per lane per pass (loads in flight)
-  float sum[NV];
 #pragma unroll
   for (int i = 0; i < NV; i++) sum[i] = 0.f;
-
-  const Pose Tl = a.Tlin, Te = a.Teval;
   const int n_off = MODE == 0 ? a.n_off : NOFF;
   const long long n_tasks = (long long)a.n * G;
   for (long long task = (long long)blockIdx.x * kLinThreads + threadIdx.x; task < n_tasks; task += (long long)gridDim.x * kLinThreads) {
@@ -450,6 +449,12 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
     }
   }
 
+}
+
+// block reduction (warp shuffles in float -> shared in double -> per-block partial), ticket, fixed-order fold by the last
+// block.  Returns true in every thread of the last block; the folded sums are then in fin[0][0..NV).
+template <int NV>
+__device__ __forceinline__ bool lin_reduce(const LinArgs& a, const float* sum, double (*fin)[kLinValues]) {
   // ---- block reduction: warp shuffles (float) -> shared (double) -> per-block partial ----
   __shared__ double sh[kLinThreads / 32][kLinValues];
   __shared__ bool is_last;
@@ -475,10 +480,9 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last) return false;
   __threadfence();
   // ---- last block: fold the per-block partials in block order (4 interleaved chains per value) ----
-  __shared__ double fin[4][kLinValues];
   {
     const int v = threadIdx.x & 31, chain = threadIdx.x >> 5;  // kLinThreads == 128 -> 4 chains
     if (v < NV) {
@@ -504,27 +508,185 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
     fin[0][threadIdx.x] = s;
   }
   __syncthreads();
+  return true;
+}
+
+// unpack the folded sums into err, H (36, column-major), b (6)
+template <bool WANT_H>
+__device__ __forceinline__ void lin_unpack(const double* s, double* out) {
+  out[0] = s[0];
+  if (WANT_H) {
+    double H[36];
+    // A (rows/cols 0..2)
+    H[0 * 6 + 0] = s[1]; H[1 * 6 + 0] = H[0 * 6 + 1] = s[2]; H[2 * 6 + 0] = H[0 * 6 + 2] = s[3];
+    H[1 * 6 + 1] = s[4]; H[2 * 6 + 1] = H[1 * 6 + 2] = s[5]; H[2 * 6 + 2] = s[6];
+    // B: H(r, 3+c) = B[r][c] (column-major index (3+c)*6 + r) and its transpose
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) {
+        H[(3 + c) * 6 + r] = s[7 + r * 3 + c];
+        H[r * 6 + (3 + c)] = s[7 + r * 3 + c];
+      }
+    // M (rows/cols 3..5)
+    H[3 * 6 + 3] = s[16]; H[4 * 6 + 3] = H[3 * 6 + 4] = s[17]; H[5 * 6 + 3] = H[3 * 6 + 5] = s[18];
+    H[4 * 6 + 4] = s[19]; H[5 * 6 + 4] = H[4 * 6 + 5] = s[20]; H[5 * 6 + 5] = s[21];
+    for (int j = 0; j < 36; j++) out[1 + j] = H[j];
+    for (int j = 0; j < 6; j++) out[37 + j] = s[22 + j];
+  }
+}
+
+// MODE: 0 = offsets from memory (DIRECT_RADIUS or anything), 1 / 7 / 27 = the reference's fixed tables.
+// G lanes share one source point and split its neighbour cells (lane s takes offsets s, s+G, ...): at 17k points a
+// one-thread-per-point mapping leaves one warp per scheduler and 27 serial dependent probes per thread; with G = 8 the
+// probes of a lane (<= 4) are issued together and the grid has 8x the warps to hide the L2 latency.
+template <int MODE, bool WANT_H, int G>
+__global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
+  constexpr int NV = WANT_H ? kLinValues : 1;
+  __shared__ double fin[4][kLinValues];
+  float sum[NV];
+  lin_accumulate<MODE, WANT_H, G>(a, a.Tlin, a.Teval, sum);
+  if (!lin_reduce<NV>(a, sum, fin)) return;
   if (threadIdx.x == 0) {
-    double* out = a.out;
-    out[0] = fin[0][0];
-    if (WANT_H) {
-      const double* s = fin[0];
-      double H[36];
-      // A (rows/cols 0..2)
-      H[0 * 6 + 0] = s[1]; H[1 * 6 + 0] = H[0 * 6 + 1] = s[2]; H[2 * 6 + 0] = H[0 * 6 + 2] = s[3];
-      H[1 * 6 + 1] = s[4]; H[2 * 6 + 1] = H[1 * 6 + 2] = s[5]; H[2 * 6 + 2] = s[6];
-      // B: H(r, 3+c) = B[r][c] (column-major index (3+c)*6 + r) and its transpose
-      for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) {
-          H[(3 + c) * 6 + r] = s[7 + r * 3 + c];
-          H[r * 6 + (3 + c)] = s[7 + r * 3 + c];
-        }
-      // M (rows/cols 3..5)
-      H[3 * 6 + 3] = s[16]; H[4 * 6 + 3] = H[3 * 6 + 4] = s[17]; H[5 * 6 + 3] = H[3 * 6 + 5] = s[18];
-      H[4 * 6 + 4] = s[19]; H[5 * 6 + 4] = H[4 * 6 + 5] = s[20]; H[5 * 6 + 5] = s[21];
-      for (int j = 0; j < 36; j++) out[1 + j] = H[j];
-      for (int j = 0; j < 6; j++) out[37 + j] = s[22 + j];
+    lin_unpack<WANT_H>(fin[0], a.out);
+    *a.ticket = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-resident optimiser: LsqRegistration::computeTransformation (lsq_registration_impl.hpp:53-79) with step_gn
+// (:106-120) / step_lm (:123-168) as a chain of evaluation kernels.  Each launch reads the phase and the two poses from
+// the state block, evaluates (linearize = lookup at x0 + H,b,err ; or error only at the candidate xi with the
+// correspondences of x0), and thread 0 of its last block advances the state machine in double -- exactly the host
+// logic, same arithmetic (lsq_math.hpp is shared).  A launch that finds phase == DONE returns at once, so the host
+// can enqueue a fixed number of launches and read the state back once.
+// ---------------------------------------------------------------------------------------------------------------
+struct LmState {
+  double x0[16], xi[16], delta[16];
+  double H[36], b[6], d[6], final_H[36];
+  double y0, lambda, nu;
+  // parameters
+  double rotation_epsilon, transformation_epsilon, lm_init_lambda_factor;
+  int max_iterations, lm_max_iterations, use_gauss_newton;
+  // progress
+  int phase;  // 0 = linearize at x0, 1 = error at xi, 2 = done
+  int it, lm_j, converged, lm_failed, n_linearize, n_error, nr_iterations;
+  Pose lin_pose, eval_pose;
+};
+enum { kLmLinearize = 0, kLmError = 1, kLmDone = 2 };
+
+__device__ __forceinline__ Pose pose_from_iso(const double* T) {
+  Pose p;
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) p.r[r * 3 + c] = (float)T[c * 4 + r];
+    p.t[r] = (float)T[12 + r];
+  }
+  return p;
+}
+
+__device__ void lm_propose(LmState* st) {  // solve (H + lambda I) d = -b, delta = exp(d), xi = delta * x0   (:134-139)
+  double Hl[36], nb[6];
+  for (int j = 0; j < 36; j++) Hl[j] = st->H[j];
+  for (int q = 0; q < 6; q++) { Hl[q * 7] += st->lambda; nb[q] = -st->b[q]; }
+  ldlt_solve6(Hl, nb, st->d);
+  Iso3d delta = se3_exp(st->d);
+  Iso3d x0;
+  for (int j = 0; j < 16; j++) x0.m[j] = st->x0[j];
+  Iso3d xi = iso_mul(delta, x0);
+  for (int j = 0; j < 16; j++) { st->delta[j] = delta.m[j]; st->xi[j] = xi.m[j]; }
+  st->eval_pose = pose_from_iso(st->xi);
+  st->phase = kLmError;
+}
+
+__device__ void lm_finish_outer(LmState* st) {  // end of step_optimize: converged_ = is_converged(delta), next outer iteration (:65-75)
+  Iso3d delta;
+  for (int j = 0; j < 16; j++) delta.m[j] = st->delta[j];
+  st->converged = is_converged(delta, st->rotation_epsilon, st->transformation_epsilon) ? 1 : 0;
+  st->it++;
+  if (st->converged || st->it >= st->max_iterations) { st->phase = kLmDone; return; }
+  st->nr_iterations = st->it;
+  st->lin_pose = pose_from_iso(st->x0);
+  st->eval_pose = st->lin_pose;
+  st->phase = kLmLinearize;
+}
+
+__device__ void lm_advance(LmState* st, const double* out /*err, H, b*/) {
+  if (st->phase == kLmLinearize) {
+    st->y0 = out[0];
+    for (int j = 0; j < 36; j++) st->H[j] = out[1 + j];
+    for (int j = 0; j < 6; j++) st->b[j] = out[37 + j];
+    st->n_linearize++;
+    if (st->use_gauss_newton) {  // step_gn
+      double nb[6];
+      for (int q = 0; q < 6; q++) nb[q] = -st->b[q];
+      ldlt_solve6(st->H, nb, st->d);
+      Iso3d delta = se3_exp(st->d), x0;
+      for (int j = 0; j < 16; j++) x0.m[j] = st->x0[j];
+      x0 = iso_mul(delta, x0);
+      for (int j = 0; j < 16; j++) { st->x0[j] = x0.m[j]; st->delta[j] = delta.m[j]; }
+      for (int j = 0; j < 36; j++) st->final_H[j] = st->H[j];
+      lm_finish_outer(st);
+      return;
     }
+    if (st->lambda < 0.0) {  // :128-130
+      double mx = 0.0;
+      for (int j = 0; j < 6; j++) mx = fmax(mx, fabs(st->H[j * 7]));
+      st->lambda = st->lm_init_lambda_factor * mx;
+    }
+    st->nu = 2.0;
+    st->lm_j = 0;
+    lm_propose(st);
+    return;
+  }
+  // phase == kLmError  (:140-164)
+  const double yi = out[0];
+  st->n_error++;
+  double den = 0.0;
+  for (int q = 0; q < 6; q++) den += st->d[q] * (st->lambda * st->d[q] - st->b[q]);
+  const double rho = (st->y0 - yi) / den;
+  if (rho < 0) {
+    Iso3d delta;
+    for (int j = 0; j < 16; j++) delta.m[j] = st->delta[j];
+    if (is_converged(delta, st->rotation_epsilon, st->transformation_epsilon)) { lm_finish_outer(st); return; }  // :151-154
+    st->lambda = st->nu * st->lambda;
+    st->nu = 2 * st->nu;
+    st->lm_j++;
+    if (st->lm_j >= st->lm_max_iterations) {  // step_lm returns false -> "lm not converged!!" (:69-72)
+      st->lm_failed = 1;
+      st->phase = kLmDone;
+      return;
+    }
+    lm_propose(st);
+    return;
+  }
+  for (int j = 0; j < 16; j++) st->x0[j] = st->xi[j];  // :161-164
+  const double f = 1.0 - pow(2.0 * rho - 1.0, 3);
+  st->lambda = st->lambda * fmax(1.0 / 3.0, f);
+  for (int j = 0; j < 36; j++) st->final_H[j] = st->H[j];
+  lm_finish_outer(st);
+}
+
+template <int MODE, int G>
+__global__ void __launch_bounds__(kLinThreads) k_lm_step(const LinArgs a, LmState* st) {
+  __shared__ double fin[4][kLinValues];
+  __shared__ double out[44];
+  const int phase = st->phase;
+  if (phase == kLmDone) return;
+  const Pose Tl = st->lin_pose, Te = st->eval_pose;
+  bool last;
+  if (phase == kLmLinearize) {
+    float sum[kLinValues];
+    lin_accumulate<MODE, true, G>(a, Tl, Te, sum);
+    last = lin_reduce<kLinValues>(a, sum, fin);
+  } else {
+    float sum[1];
+    lin_accumulate<MODE, false, G>(a, Tl, Te, sum);
+    last = lin_reduce<1>(a, sum, fin);
+  }
+  if (!last) return;
+  if (threadIdx.x == 0) {
+    if (phase == kLmLinearize) lin_unpack<true>(fin[0], out);
+    else lin_unpack<false>(fin[0], out);
+    lm_advance(st, out);
+    __threadfence();
     *a.ticket = 0u;
   }
 }

@@ -156,6 +156,11 @@ VGICP_API int vgicp_transform_source(vgicp_handle h, const double T[16], float* 
  * the read is stream-ordered on the handle's stream, the caller keeps the buffer alive until the next synchronising call */
 VGICP_API int vgicp_set_source_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, size_t stride_bytes);
 VGICP_API int vgicp_set_target_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, size_t stride_bytes);
+/* vgicp_align driver: 1 = host-driven loop over the evaluation kernels (default; one 344-byte readback per evaluation, like
+ * the reference), 0 = device-resident loop (the LM state machine runs in the last block of each evaluation kernel, the host
+ * reads one state block back per chunk of launches).  Both walk the same iterates; measured on B200 the serial double-precision
+ * LM step on one GPU thread costs about what the host round trip costs, so the host-driven loop stays the default. */
+VGICP_API int vgicp_set_align_mode(vgicp_handle h, int mode);
 /* k-NN engine used by find_*_neighbors: 0 = multi-level hash grid (default), 1 = warp-cooperative scan of the whole cloud,
  * 2 = one-thread-per-query scan (the shape of the reference's brute_force_knn.cu).  All three return identical rows. */
 VGICP_API int vgicp_set_knn_mode(vgicp_handle h, int mode);

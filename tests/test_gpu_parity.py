@@ -266,6 +266,44 @@ def test_align_matches_oracle_and_ground_truth(prepared, relative_pose, method):
     c.close()
 
 
+@pytest.mark.parametrize("method", [O.DIRECT1, O.DIRECT27, O.DIRECT_RADIUS])
+@pytest.mark.parametrize("gauss_newton", [0, 1])
+def test_device_resident_loop_matches_host_loop(prepared, method, gauss_newton):
+    """vgicp_align mode 0 (LM state machine on the device, kernel chain) and mode 1 (host-driven loop over the same kernels)
+    walk the same iterates: same counts, poses equal to ~1e-12 (libm vs CUDA double sin/cos/pow differ in the last ulp)."""
+    from fast_gicp_b200.core import Core, default_params, pose_from_c
+
+    c = Core(0)
+    _setup_pair(c, prepared, method, 1.5 if method == O.DIRECT_RADIUS else -1.0)
+    params = default_params(use_gauss_newton=gauss_newton, max_iterations=12 if gauss_newton else 64)
+    guess = np.eye(4)
+    guess[:3, 3] = [0.2, -0.1, 0.05]
+    c.set_align_mode(1)
+    host = c.align(guess, params)
+    c.set_align_mode(0)
+    dev = c.align(guess, params)
+    assert (dev.nr_iterations, dev.converged, dev.n_linearize, dev.n_compute_error, dev.lm_failed) == (
+        host.nr_iterations, host.converged, host.n_linearize, host.n_compute_error, host.lm_failed)
+    assert np.abs(pose_from_c(dev.T) - pose_from_c(host.T)).max() < 1e-10
+    assert np.abs(np.array(dev.H) - np.array(host.H)).max() <= 1e-9 * np.abs(np.array(host.H)).max()
+    c.close()
+
+
+def test_device_loop_lm_failure_and_iteration_cap(prepared):
+    """max_iterations is honoured, and a hopeless start reports the reference's 'lm not converged' state instead of hanging."""
+    from fast_gicp_b200.core import Core, default_params
+
+    c = Core(0)
+    _setup_pair(c, prepared, O.DIRECT1)
+    r = c.align(np.eye(4), default_params(max_iterations=2))
+    assert r.n_linearize == 2 and not r.converged and r.nr_iterations == 1
+    for mode in (0, 1):
+        c.set_align_mode(mode)
+        r = c.align(np.eye(4), default_params(max_iterations=0))
+        assert r.n_linearize == 0 and not r.converged
+    c.close()
+
+
 def test_align_17k_pair(pair01, relative_pose):
     """BASELINE config 2 inputs (17k-pt pair, DIRECT27, res 1.0) end to end against the oracle."""
     from fast_gicp_b200.core import Core, pose_from_c
