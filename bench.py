@@ -38,6 +38,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_REAL_STDOUT = sys.stdout
 METRIC = "registrations/sec (VGICP, ~17k-pt pairs)"
 UNIT = "registrations/s"
 
@@ -176,11 +177,17 @@ def run_reference_arm(args, w, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 # -------------------------------------------------------------------------------------------------------- GPU arm
 def main():
+    # stdout carries exactly one JSON line: route everything else that writes to fd 1 (NCCL's version banner, library
+    # chatter) to stderr and keep a private handle on the real stdout for the result.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -444,7 +451,7 @@ def main():
         "wall_ms_per_step": 1e3 * wall_s / K,
         "pose_check": {"translation": [float(x) for x in T_val[:3, 3]], "e2e_vs_resident_max_abs": float(np.abs(np.asarray(T_e2e, dtype=np.float64) - T_val).max())},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     D.finalize()
 
 
