@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "vgicp_lsq_default_params", "vgicp_align", "vgicp_transform_source",
     "vgicp_get_launch_count", "vgicp_synchronize", "vgicp_get_stream",
     "vgicp_set_source_cloud_device", "vgicp_set_target_cloud_device", "vgicp_set_profiling", "vgicp_get_profile", "vgicp_profile_category_name",
-    "vgicp_set_knn_mode", "vgicp_register", "vgicp_set_align_mode",
+    "vgicp_set_knn_mode", "vgicp_register", "vgicp_set_align_mode", "vgicp_get_fitness_score",
 ]
 PROF_NUM_CATEGORIES = 7
 
@@ -125,6 +125,7 @@ def load_library():
         "vgicp_set_profiling": [hp, C.c_int],
         "vgicp_set_knn_mode": [hp, C.c_int],
         "vgicp_set_align_mode": [hp, C.c_int],
+        "vgicp_get_fitness_score": [hp, dp, C.c_double, dp],
         "vgicp_register": [hp, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, dp, C.POINTER(LsqParams), C.POINTER(AlignResult)],
         "vgicp_get_profile": [hp, dp, C.POINTER(C.c_uint64), C.c_int],
     }
@@ -412,6 +413,12 @@ class Core:
         t = pose_to_c(T)
         self._check(self._lib.vgicp_transform_source(self._h, _dp(t), out.ctypes.data, n, stride))
         return out
+
+    def fitness_score(self, T, max_range=float("inf")):
+        t = pose_to_c(T)
+        out = C.c_double(0.0)
+        self._check(self._lib.vgicp_get_fitness_score(self._h, _dp(t), min(float(max_range), 1.7976931348623157e308), C.byref(out)))
+        return out.value
 
     def launch_count(self):
         v = C.c_uint64(0)

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <limits>
 #include <new>
 #include <string>
 #include <vector>
@@ -1047,6 +1048,31 @@ int vgicp_get_profile(vgicp_handle h, double* ms, uint64_t* launches, int capaci
 const char* vgicp_profile_category_name(int category) {
   static const char* names[VGICP_PROF_NUM_CATEGORIES] = {"unpack_points", "knn", "covariance", "voxelmap_build", "linearize", "compute_error", "other"};
   return (category >= 0 && category < VGICP_PROF_NUM_CATEGORIES) ? names[category] : "";
+}
+
+// pcl::Registration::getFitnessScore(max_range): mean squared distance from the transformed source points to their nearest
+// target point over the pairs with d^2 <= max_range (PCL compares the squared distance with max_range).
+int vgicp_get_fitness_score(vgicp_handle h, const double T[16], double max_range, double* score) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (!T || !score) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_fitness_score: null argument");
+  if (!h->source.has_pts || !h->target.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "get_fitness_score: source and target clouds required");
+  const int n = h->source.n;
+  *score = std::numeric_limits<double>::max();
+  if (n == 0 || h->target.n == 0) return VGICP_OK;
+  CU_TRY(h, h->staging.reserve((size_t)n * sizeof(float)));
+  float* d_out = reinterpret_cast<float*>(h->staging.p);
+  KLAUNCH(h, VGICP_PROF_OTHER, k_nn1_sqdist<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->source.pts.p, n, h->target.pts.p, h->target.n, to_pose(T), d_out));
+  CU_TRY(h, cudaGetLastError());
+  std::vector<float> d2(n);
+  CU_TRY(h, cudaMemcpyAsync(d2.data(), d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  double sum = 0.0;
+  long cnt = 0;
+  for (int i = 0; i < n; i++)
+    if ((double)d2[i] <= max_range) { sum += (double)d2[i]; cnt++; }
+  if (cnt > 0) *score = sum / (double)cnt;
+  return VGICP_OK;
 }
 
 int vgicp_get_launch_count(vgicp_handle h, uint64_t* launches) {

@@ -707,6 +707,32 @@ __global__ void k_correspondence_ids(const float4* __restrict__ pts, int n, cons
   }
 }
 
+// pcl::Registration::getFitnessScore support: squared distance from every transformed source point to its nearest target
+// point (tiled scan of the target through shared memory, one source point per thread).
+__global__ void __launch_bounds__(256) k_nn1_sqdist(const float4* __restrict__ src, int n_src, const float4* __restrict__ tgt, int n_tgt, const Pose T, float* __restrict__ out) {
+  __shared__ float4 tile[1024];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float3 q = make_float3(0.f, 0.f, 0.f);
+  if (i < n_src) {
+    float4 p = src[i];
+    q = transform_point(T, p.x, p.y, p.z);
+  }
+  float best = __int_as_float(0x7f800000);
+  for (int base = 0; base < n_tgt; base += 1024) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x) tile[j] = (base + j < n_tgt) ? tgt[base + j] : make_float4(1e30f, 1e30f, 1e30f, 0.f);
+    __syncthreads();
+    const int lim = min(1024, n_tgt - base);
+#pragma unroll 8
+    for (int j = 0; j < lim; j++) {
+      float4 t = tile[j];
+      float dx = t.x - q.x, dy = t.y - q.y, dz = t.z - q.z;
+      best = fminf(best, (dx * dx + dy * dy) + dz * dz);
+    }
+  }
+  if (i < n_src) out[i] = best;
+}
+
 // pcl::transformPointCloud (lsq_registration_impl.hpp:78): out = T * p, written back in the caller's stride
 __global__ void k_transform_points(const float4* __restrict__ pts, int n, const Pose T, unsigned char* __restrict__ out, size_t stride) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -246,4 +246,5 @@ class FastVGICPCuda(LsqRegistration):
         return self.final_transformation_
 
     def getFitnessScore(self, max_range=float("inf")):
-        raise NotImplementedError("getFitnessScore is PCL base-class functionality outside the accelerated path (SURVEY section 8f-3)")
+        """pcl::Registration::getFitnessScore: mean squared nearest-neighbour distance of the aligned source to the target."""
+        return self.vgicp_cuda_.fitness_score(self.final_transformation_.astype(np.float64), max_range)

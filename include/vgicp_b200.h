@@ -172,6 +172,10 @@ enum {
 VGICP_API int vgicp_set_profiling(vgicp_handle h, int enable);
 VGICP_API int vgicp_get_profile(vgicp_handle h, double* ms_per_category, uint64_t* launches_per_category, int capacity);
 VGICP_API const char* vgicp_profile_category_name(int category);
+/* pcl::Registration::getFitnessScore(max_range) for the current source/target under T (used by src/align.cpp:67 and pygicp's
+ * get_fitness_score, src/python/main.cpp:158): mean squared nearest-neighbour distance over pairs with d^2 <= max_range;
+ * DBL_MAX when no pair qualifies. */
+VGICP_API int vgicp_get_fitness_score(vgicp_handle h, const double T[16], double max_range, double* score);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 VGICP_API int vgicp_get_launch_count(vgicp_handle h, uint64_t* launches);
 VGICP_API int vgicp_synchronize(vgicp_handle h);

@@ -24,6 +24,7 @@ def _build_everything():
     import build_native as b
 
     b.build_native()
+    b.build_host_cpp()
 
 
 @pytest.fixture(scope="session")
