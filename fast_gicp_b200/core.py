@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = [
     "vgicp_get_launch_count", "vgicp_synchronize", "vgicp_get_stream",
     "vgicp_set_source_cloud_device", "vgicp_set_target_cloud_device", "vgicp_set_profiling", "vgicp_get_profile", "vgicp_profile_category_name",
     "vgicp_set_knn_mode", "vgicp_register", "vgicp_set_align_mode", "vgicp_get_fitness_score",
+    "vgicp_comm_export", "vgicp_comm_init", "vgicp_comm_shutdown", "vgicp_comm_error", "vgicp_set_source_shard", "vgicp_clear_source_shard",
 ]
 PROF_NUM_CATEGORIES = 7
 
@@ -126,6 +127,12 @@ def load_library():
         "vgicp_set_knn_mode": [hp, C.c_int],
         "vgicp_set_align_mode": [hp, C.c_int],
         "vgicp_get_fitness_score": [hp, dp, C.c_double, dp],
+        "vgicp_comm_export": [hp, C.c_void_p],
+        "vgicp_comm_init": [hp, C.c_int, C.c_int, C.c_void_p],
+        "vgicp_comm_shutdown": [hp],
+        "vgicp_comm_error": [hp, ip],
+        "vgicp_set_source_shard": [hp, C.c_size_t, C.c_size_t],
+        "vgicp_clear_source_shard": [hp],
         "vgicp_register": [hp, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, dp, C.POINTER(LsqParams), C.POINTER(AlignResult)],
         "vgicp_get_profile": [hp, dp, C.POINTER(C.c_uint64), C.c_int],
     }
@@ -413,6 +420,33 @@ class Core:
         t = pose_to_c(T)
         self._check(self._lib.vgicp_transform_source(self._h, _dp(t), out.ctypes.data, n, stride))
         return out
+
+    # ---- multi-GPU source sharding
+    def comm_export(self):
+        buf = (C.c_ubyte * 64)()
+        self._check(self._lib.vgicp_comm_export(self._h, buf))
+        return bytes(buf)
+
+    def comm_init(self, rank, nranks, all_handles):
+        """all_handles: nranks x 64 bytes, rank order (all-gathered from comm_export())."""
+        blob = b"".join(all_handles)
+        assert len(blob) == 64 * nranks
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self._lib.vgicp_comm_init(self._h, int(rank), int(nranks), arr))
+
+    def comm_shutdown(self):
+        self._check(self._lib.vgicp_comm_shutdown(self._h))
+
+    def comm_error(self):
+        v = C.c_int(0)
+        self._check(self._lib.vgicp_comm_error(self._h, C.byref(v)))
+        return v.value
+
+    def set_source_shard(self, begin, end):
+        self._check(self._lib.vgicp_set_source_shard(self._h, int(begin), int(end)))
+
+    def clear_source_shard(self):
+        self._check(self._lib.vgicp_clear_source_shard(self._h))
 
     def fitness_score(self, T, max_range=float("inf")):
         t = pose_to_c(T)

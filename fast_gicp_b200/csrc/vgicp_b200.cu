@@ -97,6 +97,12 @@ struct vgicp_context {
 
   DevBuf<unsigned char> staging;
   DevBuf<unsigned char> knn_scratch;
+  // multi-GPU source sharding
+  CommMailbox* comm_box = nullptr;               // this rank's mailbox (device memory, IPC-exported)
+  CommMailbox* comm_peers[kCommMaxRanks] = {};   // mapped peer mailboxes (own included)
+  int comm_rank = 0, comm_ranks = 0;
+  unsigned long long comm_seq = 0;
+  int shard_begin = 0, shard_end = -1;           // evaluations cover source points [begin, end)
   int align_mode = 1;  // 1 = host-driven loop over the evaluation kernels (default: faster today), 0 = device-resident LM chain
   LmState* d_lm = nullptr;
   LmState* h_lm = nullptr;  // pinned
@@ -362,7 +368,11 @@ LinLaunch make_lin_launch(vgicp_handle h) {
   VoxelMap& m = h->map;
   LinLaunch L;
   LinArgs& a = L.a;
-  a.pts = s.pts.p; a.covA = s.covA.p; a.covB = s.covB.p; a.n = s.n;
+  const int sb = h->shard_end >= 0 ? h->shard_begin : 0;
+  const int se = h->shard_end >= 0 ? (h->shard_end < s.n ? h->shard_end : s.n) : s.n;
+  a.pts = s.pts.p + sb; a.covA = s.covA.p + sb; a.covB = s.covB.p + sb; a.n = se > sb ? se - sb : 0;
+  a.comm_ranks = h->comm_ranks; a.comm_rank = h->comm_rank; a.comm_seq = 0;
+  for (int r = 0; r < kCommMaxRanks; r++) a.comm_peers[r] = h->comm_peers[r];
   a.buckets = m.buckets.p; a.mask = (unsigned)(m.num_buckets - 1); a.max_scan = m.max_scan; a.vox = m.vox.p;
   a.offsets = h->d_offsets.p; a.n_off = (int)h->h_offsets.size(); a.res = m.res;
   a.Tlin = h->lin; a.Teval = h->lin;
@@ -370,9 +380,9 @@ LinLaunch make_lin_launch(vgicp_handle h) {
   // lanes per source point: split the neighbour cells of a point over G lanes while the cloud is too small to fill the
   // GPU with one thread per point (latency-bound regime); one lane per point once it is large (ALU/bandwidth-bound regime)
   const int n_off = a.n_off;
-  const bool wide = s.n < 400000 && n_off > 1;
+  const bool wide = a.n < 400000 && n_off > 1;
   L.G = !wide ? 1 : (n_off <= 7 ? 4 : 8);
-  long long tasks = (long long)(s.n > 0 ? s.n : 1) * L.G;
+  long long tasks = (long long)(a.n > 0 ? a.n : 1) * L.G;
   long long grid = (tasks + kLinThreads - 1) / kLinThreads;
   L.grid = (int)(grid > kLinMaxBlocks ? kLinMaxBlocks : grid);
   return L;
@@ -383,6 +393,7 @@ int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H) {
   LinLaunch L = make_lin_launch(h);
   LinArgs& a = L.a;
   a.Teval = Teval;
+  a.comm_seq = h->comm_seq++;
   const int grid = L.grid, G = L.G;
 #define LAUNCH_LIN_G(MODE, GG)                                                           \
   do {                                                                                   \
@@ -512,6 +523,8 @@ int vgicp_destroy(vgicp_handle h) {
   h->d_offsets.release();
   h->staging.release();
   h->knn_scratch.release();
+  if (h->comm_ranks > 1) vgicp_comm_shutdown(h);
+  if (h->comm_box) cudaFree(h->comm_box);
   h->partials.release();
   h->corr_ids.release();
   if (h->d_ticket) cudaFree(h->d_ticket);
@@ -842,7 +855,7 @@ int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* 
   if (!h->source.has_pts || !h->source.has_cov) return fail(h, VGICP_ERR_BAD_STATE, "align: source points and covariances required");
   if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "align: target voxel map not built");
 
-  if (h->align_mode == 0) {
+  if (h->align_mode == 0 && h->comm_ranks <= 1) {
     // device-resident loop: initialise the state block, enqueue evaluation links, read the state back once per chunk
     LmState* st = h->h_lm;
     memset(st, 0, sizeof(LmState));
@@ -1002,6 +1015,82 @@ int vgicp_set_target_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, 
   h->target.has_cov = false;
   h->map.built = false;
   return set_cloud(h, h->target, d_xyz, n, stride_bytes, true);
+}
+
+// ---- multi-GPU: source sharding with an in-kernel exchange of the linear system over NVLink peer memory ----
+int vgicp_comm_export(vgicp_handle h, unsigned char* handle64) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (!handle64) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "comm_export: null buffer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!h->comm_box) {
+    CU_TRY(h, cudaMalloc(&h->comm_box, sizeof(CommMailbox)));
+    CU_TRY(h, cudaMemset(h->comm_box, 0, sizeof(CommMailbox)));
+  }
+  cudaIpcMemHandle_t ipc;
+  CU_TRY(h, cudaIpcGetMemHandle(&ipc, h->comm_box));
+  memcpy(handle64, &ipc, 64);
+  return VGICP_OK;
+}
+
+int vgicp_comm_init(vgicp_handle h, int rank, int nranks, const unsigned char* all_handles) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (nranks < 1 || nranks > kCommMaxRanks || rank < 0 || rank >= nranks || !all_handles) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "comm_init: need 1 <= nranks <= 8 and all handles");
+  if (!h->comm_box) return fail(h, VGICP_ERR_BAD_STATE, "comm_init: call vgicp_comm_export first");
+  for (int r = 0; r < nranks; r++) {
+    if (r == rank) { h->comm_peers[r] = h->comm_box; continue; }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, all_handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(h, VGICP_ERR_COMM, std::string("comm_init: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    h->comm_peers[r] = reinterpret_cast<CommMailbox*>(p);
+  }
+  h->comm_rank = rank;
+  h->comm_ranks = nranks;
+  h->comm_seq = 0;
+  return VGICP_OK;
+}
+
+int vgicp_comm_shutdown(vgicp_handle h) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int r = 0; r < h->comm_ranks; r++)
+    if (r != h->comm_rank && h->comm_peers[r]) cudaIpcCloseMemHandle(h->comm_peers[r]);
+  for (int r = 0; r < kCommMaxRanks; r++) h->comm_peers[r] = nullptr;
+  h->comm_ranks = 0;
+  h->comm_rank = 0;
+  return VGICP_OK;
+}
+
+int vgicp_comm_error(vgicp_handle h, int* error) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (!error) return VGICP_ERR_INVALID_ARGUMENT;
+  *error = 0;
+  if (h->comm_box) {
+    CommMailbox tmp;
+    CU_TRY(h, cudaMemcpy(&tmp, h->comm_box, sizeof(CommMailbox), cudaMemcpyDeviceToHost));
+    *error = tmp.error;
+  }
+  return VGICP_OK;
+}
+
+int vgicp_set_source_shard(vgicp_handle h, size_t begin, size_t end) {
+  CHECK_HANDLE(h);
+  if (end < begin) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_source_shard: end < begin");
+  h->shard_begin = (int)begin;
+  h->shard_end = (int)end;
+  return VGICP_OK;
+}
+
+int vgicp_clear_source_shard(vgicp_handle h) {
+  CHECK_HANDLE(h);
+  h->shard_begin = 0;
+  h->shard_end = -1;
+  return VGICP_OK;
 }
 
 int vgicp_set_align_mode(vgicp_handle h, int mode) {

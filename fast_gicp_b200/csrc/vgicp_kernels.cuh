@@ -34,6 +34,14 @@ struct Pose {      // float image of an Eigen::Isometry3f: R row-major here, t
   float t[3];
 };
 
+constexpr int kCommMaxRanks = 8;
+// one per rank, in that rank's device memory, mapped into every peer with CUDA IPC
+struct CommMailbox {
+  double vals[2][kCommMaxRanks][32];                 // [seq & 1][sender][28 sums]
+  volatile unsigned long long flags[2][kCommMaxRanks];  // [seq & 1][sender] = seq + 1 once the sender's values are visible
+  volatile int error;                                // set when a wait times out
+};
+
 struct VoxelRec {
   float4 mean_n;  // mean xyz, num_points as int bits in w
   float4 c0;      // cxx cxy cxz cyy
@@ -267,6 +275,12 @@ struct LinArgs {
   double* partials;       // [gridDim.x][kLinValues]
   unsigned int* ticket;   // zero before first launch; reset by the last block
   double* out;            // [43]: err, H (36, column-major), b (6)
+  // source sharded over several GPUs: the folded sums of this rank are exchanged with the peers by the last
+  // block itself, through mailboxes in peer memory (NVLink P2P stores), and summed in rank order
+  int comm_ranks;         // 0/1 = single GPU
+  int comm_rank;
+  unsigned long long comm_seq;   // evaluation number (same on every rank), selects the mailbox half
+  CommMailbox* comm_peers[kCommMaxRanks];  // peers' mailboxes (index = rank; own mailbox included)
 };
 
 __device__ __forceinline__ int lookup_voxel(const int4* __restrict__ buckets, unsigned mask, int max_scan, uint64_t h, int cx, int cy, int cz) {
@@ -508,6 +522,36 @@ __device__ __forceinline__ bool lin_reduce(const LinArgs& a, const float* sum, d
     fin[0][threadIdx.x] = s;
   }
   __syncthreads();
+  if (a.comm_ranks > 1) {
+    // ---- fused exchange: store this rank's sums into every peer's mailbox over NVLink, publish, wait for the peers,
+    // add in rank order (identical doubles in identical order on every rank -> identical LM decisions everywhere) ----
+    const int half = (int)(a.comm_seq & 1ULL);
+    const unsigned long long tag = a.comm_seq + 1ULL;
+    if (threadIdx.x < NV) {
+      const double mine = fin[0][threadIdx.x];
+      for (int p = 0; p < a.comm_ranks; p++) a.comm_peers[p]->vals[half][a.comm_rank][threadIdx.x] = mine;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < a.comm_ranks) {
+      a.comm_peers[threadIdx.x]->flags[half][a.comm_rank] = tag;  // one publisher thread per peer
+      __threadfence_system();
+      CommMailbox* me = a.comm_peers[a.comm_rank];
+      long long spins = 0;
+      while (me->flags[half][threadIdx.x] != tag) {  // thread q waits for rank q
+        if (++spins > (1LL << 31)) { me->error = 1; break; }
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < NV) {
+      const CommMailbox* me = a.comm_peers[a.comm_rank];
+      double s = 0.0;
+      for (int q = 0; q < a.comm_ranks; q++) s += *reinterpret_cast<const volatile double*>(&me->vals[half][q][threadIdx.x]);
+      fin[0][threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
   return true;
 }
 

@@ -156,6 +156,18 @@ VGICP_API int vgicp_transform_source(vgicp_handle h, const double T[16], float* 
  * the read is stream-ordered on the handle's stream, the caller keeps the buffer alive until the next synchronising call */
 VGICP_API int vgicp_set_source_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, size_t stride_bytes);
 VGICP_API int vgicp_set_target_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, size_t stride_bytes);
+/* ---- multi-GPU source sharding (not in the reference, which is single-GPU) --------------------------------
+ * Every rank (one process per GPU) holds the whole target and voxel map and evaluates only a slice of the source
+ * (vgicp_set_source_shard); the last block of each evaluation kernel stores its 28 folded sums into every peer's mailbox over
+ * NVLink peer memory, waits for the peers' sums and adds them in rank order, so vgicp_compute_error / vgicp_align return the
+ * same H, b, err on every rank.  Setup: each rank calls vgicp_comm_export, the 64-byte handles are all-gathered by any host
+ * transport (torch.distributed, MPI, files), then vgicp_comm_init.  Ranks must issue the same sequence of evaluations. */
+VGICP_API int vgicp_comm_export(vgicp_handle h, unsigned char* handle64);
+VGICP_API int vgicp_comm_init(vgicp_handle h, int rank, int nranks, const unsigned char* all_handles /* nranks x 64 bytes */);
+VGICP_API int vgicp_comm_shutdown(vgicp_handle h);
+VGICP_API int vgicp_comm_error(vgicp_handle h, int* error);  /* 1 when a wait for a peer timed out */
+VGICP_API int vgicp_set_source_shard(vgicp_handle h, size_t begin, size_t end);  /* evaluations cover source points [begin, end) */
+VGICP_API int vgicp_clear_source_shard(vgicp_handle h);
 /* vgicp_align driver: 1 = host-driven loop over the evaluation kernels (default; one 344-byte readback per evaluation, like
  * the reference), 0 = device-resident loop (the LM state machine runs in the last block of each evaluation kernel, the host
  * reads one state block back per chunk of launches).  Both walk the same iterates; measured on B200 the serial double-precision
