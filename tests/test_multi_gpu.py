@@ -42,10 +42,11 @@ def test_sharded_evaluation_matches_single_gpu():
     res = run_workers(world)
     for r in res:
         assert r["comm_error"] == 0
-        # the exchanged system equals the unsharded one (double sums, different association)
-        assert r["H_rel_diff_vs_full"] < 1e-12 and r["b_rel_diff_vs_full"] < 1e-10 and r["err_rel_diff_vs_full"] < 1e-12 and r["err_only_rel"] < 1e-12
+        # the exchanged system equals the unsharded one up to the float rounding of the per-warp partial sums (sharding changes
+        # which points share a warp; block and rank level sums are double)
+        assert r["H_rel_diff_vs_full"] < 1e-6 and r["b_rel_diff_vs_full"] < 1e-5 and r["err_rel_diff_vs_full"] < 1e-6 and r["err_only_rel"] < 1e-6
         assert r["converged"] and r["iters"][0] == r["iters"][1]
-        assert np.abs(np.array(r["T"]) - np.array(r["T_full"])).max() < 1e-9
+        assert np.abs(np.array(r["T"]) - np.array(r["T_full"])).max() < 1e-6
     # every rank holds bit-identical sums (same doubles added in rank order)
     for r in res[1:]:
         assert r["H_sum"] == res[0]["H_sum"] and r["b"] == res[0]["b"] and r["err"] == res[0]["err"] and r["T"] == res[0]["T"]
