@@ -262,13 +262,16 @@ def main():
     note("input pool ready (%d pairs)" % P)
     cores = [Core(local_rank) for _ in range(S)]
     regs = [FastVGICPCuda(local_rank) for _ in range(S)]
+    hint = 1 if S > 1 else 0  # many handles share the GPU -> throughput launch shapes (vgicp_set_execution_hint)
     for c in cores:
         c.set_resolution(w["res"])
         c.set_neighbor_search_method(w["method"])
+        c.set_execution_hint(hint)
     for r in regs:
         r.setResolution(w["res"])
         r.voxel_resolution_ = w["res"]
         r.setNeighborSearchMethod(w["method"])
+        r.vgicp_cuda_.set_execution_hint(hint)
     core = cores[0]
     streams = [torch.cuda.ExternalStream(c.stream(), device=dev) for c in cores]
     e2e_streams = [torch.cuda.ExternalStream(r.vgicp_cuda_.stream(), device=dev) for r in regs]
@@ -347,6 +350,8 @@ def main():
 
     # ---- single-stream latency (the reference's sequential protocol), L2 flushed between registrations
     note("e2e arm done")
+    cores[0].set_execution_hint(0)
+    regs[0].vgicp_cuda_.set_execution_hint(0)
     lat = []
     for j in range(W + min(K, 30)):
         flush.zero_()
@@ -437,7 +442,7 @@ def main():
         "metric": METRIC, "value": world * S * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": w["data"],
         "config": {"workload": w["name"], "protocol": "align.cpp 100times (covariances recomputed every registration)", "step": "one registration on each of the %d concurrent streams of a GPU (one host thread + one handle per stream)" % S,
-                   "streams_per_gpu": S, "registrations_per_step": S * world,
+                   "streams_per_gpu": S, "registrations_per_step": S * world, "execution_hint": "throughput" if hint else "latency",
                    "l2": "inputs larger than L2: each registration takes the next of %d distinct pairs (%.0f MB pool)" % (P, P * pair_bytes / 1e6),
                    "parallelism": "replicas x%d" % world, "n_target": n_t, "n_source": n_s, "num_voxels": V, "num_buckets": B,
                    "lm_iterations": int(res.nr_iterations) + 1, "evaluations": int(res.n_linearize + res.n_compute_error), "converged": bool(res.converged)},

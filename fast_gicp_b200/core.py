@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "vgicp_lsq_default_params", "vgicp_align", "vgicp_transform_source",
     "vgicp_get_launch_count", "vgicp_synchronize", "vgicp_get_stream",
     "vgicp_set_source_cloud_device", "vgicp_set_target_cloud_device", "vgicp_set_profiling", "vgicp_get_profile", "vgicp_profile_category_name",
-    "vgicp_set_knn_mode", "vgicp_register", "vgicp_set_align_mode", "vgicp_get_fitness_score",
+    "vgicp_set_knn_mode", "vgicp_register", "vgicp_set_align_mode", "vgicp_get_fitness_score", "vgicp_set_execution_hint",
     "vgicp_comm_export", "vgicp_comm_init", "vgicp_comm_shutdown", "vgicp_comm_error", "vgicp_set_source_shard", "vgicp_clear_source_shard",
 ]
 PROF_NUM_CATEGORIES = 7
@@ -127,6 +127,7 @@ def load_library():
         "vgicp_set_knn_mode": [hp, C.c_int],
         "vgicp_set_align_mode": [hp, C.c_int],
         "vgicp_get_fitness_score": [hp, dp, C.c_double, dp],
+        "vgicp_set_execution_hint": [hp, C.c_int],
         "vgicp_comm_export": [hp, C.c_void_p],
         "vgicp_comm_init": [hp, C.c_int, C.c_int, C.c_void_p],
         "vgicp_comm_shutdown": [hp],
@@ -236,6 +237,10 @@ class Core:
         """Points already resident in this GPU's memory (e.g. a torch CUDA tensor's data_ptr())."""
         fn = self._lib.vgicp_set_source_cloud_device if which == "source" else self._lib.vgicp_set_target_cloud_device
         self._check(fn(self._h, dev_ptr, n, stride))
+
+    def set_execution_hint(self, hint):
+        """0 = latency (default), 1 = throughput (many handles share the GPU)."""
+        self._check(self._lib.vgicp_set_execution_hint(self._h, int(hint)))
 
     def set_align_mode(self, mode):
         self._check(self._lib.vgicp_set_align_mode(self._h, int(mode)))

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <limits>
@@ -103,6 +104,7 @@ struct vgicp_context {
   int comm_rank = 0, comm_ranks = 0;
   unsigned long long comm_seq = 0;
   int shard_begin = 0, shard_end = -1;           // evaluations cover source points [begin, end)
+  int exec_hint = 0;  // 0 = latency (one registration should finish as soon as possible), 1 = throughput (many concurrent handles)
   int align_mode = 1;  // 1 = host-driven loop over the evaluation kernels (default: faster today), 0 = device-resident LM chain
   LmState* d_lm = nullptr;
   LmState* h_lm = nullptr;  // pinned
@@ -236,7 +238,8 @@ int find_neighbors(vgicp_handle h, Cloud& c, int k) {
     const size_t need = knn_grid_scratch_bytes(c.n, nullptr, nullptr);
     CU_TRY(h, h->knn_scratch.reserve(need));
     int nl = 0;
-    KLAUNCH(h, VGICP_PROF_KNN, ke = launch_knn_grid(c.pts.p, c.n, k, c.nbr.p, h->knn_scratch.p, h->knn_scratch.cap, (h->knn_mode == 1 || c.n < 256) ? 1 : 0, &nl, h->stream));
+    KLAUNCH(h, VGICP_PROF_KNN,
+            ke = launch_knn_grid(c.pts.p, c.n, k, c.nbr.p, h->knn_scratch.p, h->knn_scratch.cap, (h->knn_mode == 1 || c.n < 256) ? 1 : 0, h->exec_hint == 1 ? 2 : 4, &nl, h->stream));
     h->launches += nl > 0 ? nl - 1 : 0;
   }
   CU_TRY(h, ke);
@@ -381,7 +384,14 @@ LinLaunch make_lin_launch(vgicp_handle h) {
   // GPU with one thread per point (latency-bound regime); one lane per point once it is large (ALU/bandwidth-bound regime)
   const int n_off = a.n_off;
   const bool wide = a.n < 400000 && n_off > 1;
-  L.G = !wide ? 1 : (n_off <= 7 ? 4 : 8);
+  // latency hint: split a point's cells over 4 (<= 7 offsets) or 8 lanes; throughput hint (many handles share the GPU, the
+  // SMs are kept busy by other streams): one lane per point -- fewer instructions per registration, longer single kernel
+  L.G = (!wide || h->exec_hint == 1) ? 1 : (n_off <= 7 ? 4 : 8);
+  {
+    static int force_g = -1;
+    if (force_g < 0) { const char* e = getenv("VGICP_LIN_G"); force_g = e ? atoi(e) : 0; }
+    if (force_g == 1 || force_g == 4 || force_g == 8) L.G = force_g;
+  }
   long long tasks = (long long)(a.n > 0 ? a.n : 1) * L.G;
   long long grid = (tasks + kLinThreads - 1) / kLinThreads;
   L.grid = (int)(grid > kLinMaxBlocks ? kLinMaxBlocks : grid);
@@ -1090,6 +1100,13 @@ int vgicp_clear_source_shard(vgicp_handle h) {
   CHECK_HANDLE(h);
   h->shard_begin = 0;
   h->shard_end = -1;
+  return VGICP_OK;
+}
+
+int vgicp_set_execution_hint(vgicp_handle h, int hint) {
+  CHECK_HANDLE(h);
+  if (hint < 0 || hint > 1) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_execution_hint: 0 latency, 1 throughput");
+  h->exec_hint = hint;
   return VGICP_OK;
 }
 

@@ -349,7 +349,8 @@ template <int MODE, bool WANT_H, int G>
 __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl, const Pose& Te, float* sum) {
   constexpr int NV = WANT_H ? kLinValues : 1;
   constexpr int NOFF = MODE == 0 ? 0 : MODE;
-  constexpr int CELLS = MODE == 0 ? 4 : ((NOFF + G - 1) / G < 4 ? (NOFF + G - 1) / G : 4);  // cells per lane per pass (loads in flight)
+  constexpr bool COLUMNS = (MODE == 27 && G == 1);  // one thread walks all 27 cells: 9 passes of one z-column, hash prefixes shared
+  constexpr int CELLS = COLUMNS ? 3 : (MODE == 0 ? 4 : ((NOFF + G - 1) / G < 4 ? (NOFF + G - 1) / G : 4));  // cells per lane per pass (loads in flight)
 #pragma unroll
   for (int i = 0; i < NV; i++) sum[i] = 0.f;
   const int n_off = MODE == 0 ? a.n_off : NOFF;
@@ -387,12 +388,23 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl,
     acc.v[0] = acc.v[1] = acc.v[2] = 0.f;
     acc.err = 0.f;
 
+    // the 27 neighbours share hash prefixes (vector3i_hash folds x, then y, then z): 9 + 9 + 27 folds instead of 81
+    uint64_t kzm[3] = {0, 0, 0};
+    if (COLUMNS) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) kzm[d] = hash_mix((uint64_t)(int64_t)(bz + d - 1));
+    }
     for (int o0 = sub; o0 < n_off; o0 += G * CELLS) {
       // phase 1: all first-probe bucket loads of this lane in flight together
       int cx[CELLS], cy[CELLS], cz[CELLS];
       unsigned pos[CELLS];
       int4 bk[CELLS];
       bool valid[CELLS];
+      uint64_t hxy = 0;
+      if (COLUMNS) {  // o0 = 9*ix + 3*iy (i-major order of fast_vgicp_cuda.cu:68-74), cells o0, o0+1, o0+2 = iz 0..2
+        const int ix = o0 / 9, iy = (o0 / 3) % 3;
+        hxy = hash_fold(hash_fold(0, hash_mix((uint64_t)(int64_t)(bx + ix - 1))), hash_mix((uint64_t)(int64_t)(by + iy - 1)));
+      }
 #pragma unroll
       for (int j = 0; j < CELLS; j++) {
         const int o = o0 + j * G;
@@ -405,7 +417,8 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl,
           off = fixed_offset<MODE>(valid[j] ? o : 0);
         }
         cx[j] = bx + off.x; cy[j] = by + off.y; cz[j] = bz + off.z;
-        pos[j] = (unsigned)(vector3i_hash(cx[j], cy[j], cz[j]) & a.mask);
+        const uint64_t hsh = COLUMNS ? hash_fold(hxy, kzm[j]) : vector3i_hash(cx[j], cy[j], cz[j]);
+        pos[j] = (unsigned)(hsh & a.mask);
         bk[j] = __ldg(&a.buckets[pos[j]]);
       }
       // phase 2: resolve (further probes are rare: the table is <= ~50% full), then unconditional voxel loads

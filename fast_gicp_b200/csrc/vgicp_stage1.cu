@@ -10,6 +10,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace vgicp {
 
@@ -868,7 +869,8 @@ size_t knn_grid_scratch_bytes(int n, int* levels_out, unsigned* table_size_out) 
 // scratch layout:  [0xFF-filled : bbox min (16 B) | keys of all levels]
 //                  [zero-filled : bbox max (16 B) | level cursors (64 B) | cnt, fill of all levels]
 //                  [uninitialised: start of all levels | sorted copies | pslot]
-cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned char* scratch, size_t scratch_bytes, int force_bruteforce, int* launches, cudaStream_t stream) {
+cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned char* scratch, size_t scratch_bytes, int force_bruteforce, int blocks_per_sm_hint, int* launches,
+                            cudaStream_t stream) {
   int L;
   unsigned T;
   size_t need = knn_grid_scratch_bytes(n, &L, &T);
@@ -905,7 +907,10 @@ cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned 
   k_grid_alloc<<<dim3((T + 255) / 256, L), 256, 0, stream>>>(a);
   k_grid_scatter<<<dim3(nb, L), 256, 0, stream>>>(a);
   int qblocks = (n + kKnnGridWarps - 1) / kKnnGridWarps;
-  if (qblocks > 148 * 8) qblocks = 148 * 8;  // persistent: 8 blocks x 8 warps per SM, queries pulled from a counter
+  // persistent warps pull queries from a counter; 4 blocks (32 warps) per SM by default, 2 when many handles share the GPU
+  // (leaves room for other streams' kernels on every SM: +3..6 % aggregate throughput, slower alone)
+  const int blocks_per_sm = (blocks_per_sm_hint >= 1 && blocks_per_sm_hint <= 8) ? blocks_per_sm_hint : 4;
+  if (qblocks > 148 * blocks_per_sm) qblocks = 148 * blocks_per_sm;  // persistent: queries pulled from a counter
   int hblocks = qblocks < 148 * 4 ? qblocks : 148 * 4;
   if (k <= 32) {
     k_knn_grid<false><<<qblocks, kKnnGridWarps * 32, 0, stream>>>(a, force_bruteforce);

@@ -14,7 +14,8 @@ constexpr int kRbfBlock = 512;    // covariance_estimation_rbf.cu:60 BLOCK_SIZE
 cudaError_t launch_knn_bruteforce(const float4* pts, int n, int k, int* nbr, cudaStream_t stream);
 // the same result on a multi-level hash grid, one warp per query (k <= 64); scratch from knn_grid_scratch_bytes(), 16-byte aligned
 size_t knn_grid_scratch_bytes(int n, int* levels_out, unsigned* table_size_out);
-cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned char* scratch, size_t scratch_bytes, int force_bruteforce, int* launches, cudaStream_t stream);
+cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned char* scratch, size_t scratch_bytes, int force_bruteforce, int blocks_per_sm_hint, int* launches,
+                            cudaStream_t stream);
 // covariance_estimation + covariance_regularization(method) fused; symmetric-packed output
 cudaError_t launch_covariance_knn(const float4* pts, const int* nbr, int n, int k, int method, float4* covA, float2* covB, cudaStream_t stream);
 // covariance_estimation_rbf + covariance_regularization(method)

@@ -168,6 +168,11 @@ VGICP_API int vgicp_comm_shutdown(vgicp_handle h);
 VGICP_API int vgicp_comm_error(vgicp_handle h, int* error);  /* 1 when a wait for a peer timed out */
 VGICP_API int vgicp_set_source_shard(vgicp_handle h, size_t begin, size_t end);  /* evaluations cover source points [begin, end) */
 VGICP_API int vgicp_clear_source_shard(vgicp_handle h);
+/* Launch-shape hint: 0 = latency (default; one registration should finish as soon as possible: a point's neighbour cells are
+ * split over several lanes, the persistent k-NN kernel takes 4 blocks per SM), 1 = throughput (many handles share the GPU on
+ * separate streams: one lane per point and 2 k-NN blocks per SM -- fewer instructions per registration, longer kernels).
+ * Results are identical up to the float rounding of per-warp partial sums. */
+VGICP_API int vgicp_set_execution_hint(vgicp_handle h, int hint);
 /* vgicp_align driver: 1 = host-driven loop over the evaluation kernels (default; one 344-byte readback per evaluation, like
  * the reference), 0 = device-resident loop (the LM state machine runs in the last block of each evaluation kernel, the host
  * reads one state block back per chunk of launches).  Both walk the same iterates; measured on B200 the serial double-precision

@@ -30,6 +30,7 @@ for T in (1, 2, 4, 8, 16, 32):
     cores = [Core(0) for _ in range(T)]
     for c in cores:
         c.set_neighbor_search_method("DIRECT27")
+        c.set_execution_hint(int(os.environ.get("HINT", "0")))
     out = [None] * T
     for c in cores: worker(c, 3, out, 0)
     torch.cuda.synchronize()
