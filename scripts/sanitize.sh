@@ -1,0 +1,23 @@
+#!/bin/bash
+# compute-sanitizer passes over the hot path (run under gpurun): memcheck + racecheck + synccheck on one full registration
+# per k-NN engine / neighbour mode.  Output: gpurun_out/sanitizer_*.log
+set -u
+cat > /tmp/san_driver.py <<'PY'
+import sys, numpy as np
+sys.path.insert(0, ".")
+from fast_gicp_b200.core import Core
+d = np.load("tests/golden/pair_0p2.npz")
+tgt, src = d["target"][::3].copy(), d["source"][::3].copy()
+for method, knn_mode, align_mode, hint in (("DIRECT27", 0, 1, 0), ("DIRECT7", 0, 0, 1), ("DIRECT1", 1, 1, 0), ("DIRECT_RADIUS", 0, 1, 1)):
+    c = Core(0)
+    c.set_neighbor_search_method(method, 1.5)
+    c.set_knn_mode(knn_mode); c.set_align_mode(align_mode); c.set_execution_hint(hint)
+    r = c.register(tgt, src)
+    c.calculate_source_covariances_rbf(3)
+    print(method, "converged", bool(r.converged), "fitness", c.fitness_score(np.eye(4)))
+    c.close()
+PY
+for tool in memcheck racecheck synccheck; do
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_driver.py > gpurun_out/sanitizer_$tool.log 2>&1
+  echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer_$tool.log | tail -1)"
+done
