@@ -53,12 +53,22 @@ struct Cloud {
   int k = 0;           // neighbours per point currently stored (0 = none)
   bool has_pts = false;
   bool has_cov = false;
-  void release() { pts.release(); nbr.release(); covA.release(); covB.release(); }
+  // each cloud has its own stream: the stage-1 work of target and source overlaps on the GPU; `ready` marks the end of the
+  // last operation enqueued for this cloud
+  cudaStream_t st = nullptr;
+  cudaEvent_t ready = nullptr;
+  DevBuf<unsigned char> staging;
+  DevBuf<unsigned char> knn_scratch;
+  void release() { pts.release(); nbr.release(); covA.release(); covB.release(); staging.release(); knn_scratch.release(); }
 };
 
 struct VoxelMap {
   bool created = false;  // GaussianVoxelMap object exists (keeps its first resolution)
   bool built = false;
+  bool pending = false;    // first insertion attempt enqueued, outcome not yet read (voxelmap_finish completes the build)
+  int pending_B = 0;
+  bool v_pending = false;  // num_voxels still in flight
+  cudaEvent_t ev_attempt = nullptr, ev_done = nullptr;
   float res = 1.0f;
   int init_num_buckets = 8192;  // gaussian_voxelmap.cuh:20
   int max_scan = 10;            // gaussian_voxelmap.cuh:20
@@ -96,8 +106,9 @@ struct vgicp_context {
   bool has_lin = false;
   Pose lin;  // linearized_x (float)
 
-  DevBuf<unsigned char> staging;
-  DevBuf<unsigned char> knn_scratch;
+  DevBuf<unsigned char> staging;    // main-stream scratch (transform_source, fitness score)
+  cudaStream_t stream_b = nullptr;  // second cloud stream
+  cudaEvent_t ev_copy = nullptr;    // "host buffer consumed" marker of set_cloud
   // multi-GPU source sharding
   CommMailbox* comm_box = nullptr;               // this rank's mailbox (device memory, IPC-exported)
   CommMailbox* comm_peers[kCommMaxRanks] = {};   // mapped peer mailboxes (own included)
@@ -143,25 +154,26 @@ cudaEvent_t prof_event(vgicp_handle h) {
   cudaEventCreate(&e);
   return e;
 }
-inline void prof_begin(vgicp_handle h, int cat) {
+inline void prof_begin(vgicp_handle h, int cat, cudaStream_t st) {
   h->prof_launches[cat]++;
   if (!h->prof_on) return;
   vgicp_context::ProfRec r{cat, prof_event(h), prof_event(h)};
-  cudaEventRecord(r.a, h->stream);
+  cudaEventRecord(r.a, st);
   h->prof_pending.push_back(r);
 }
-inline void prof_end(vgicp_handle h) {
+inline void prof_end(vgicp_handle h, cudaStream_t st) {
   if (!h->prof_on) return;
-  cudaEventRecord(h->prof_pending.back().b, h->stream);
+  cudaEventRecord(h->prof_pending.back().b, st);
 }
-// every kernel launch of the library goes through here: counts it, optionally brackets it with events
-#define KLAUNCH(h, cat, ...) \
-  do {                       \
-    prof_begin(h, cat);      \
-    __VA_ARGS__;             \
-    prof_end(h);             \
-    (h)->launches++;         \
+// every kernel launch of the library goes through here: counts it, optionally brackets it with events on its stream
+#define KLAUNCH_ST(h, st, cat, ...) \
+  do {                              \
+    prof_begin(h, cat, st);         \
+    __VA_ARGS__;                    \
+    prof_end(h, st);                \
+    (h)->launches++;                \
   } while (0)
+#define KLAUNCH(h, cat, ...) KLAUNCH_ST(h, (h)->stream, cat, __VA_ARGS__)
 
 #define CU_TRY(h, expr)                                                                                       \
   do {                                                                                                        \
@@ -204,16 +216,20 @@ int set_cloud(vgicp_handle h, Cloud& c, const float* xyz, size_t n, size_t strid
   c.has_pts = true;
   if (n == 0) return VGICP_OK;
   if (on_device) {  // caller's buffer already lives in this GPU's memory: read it in place (stream-ordered)
-    KLAUNCH(h, VGICP_PROF_UNPACK, k_unpack_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(reinterpret_cast<const unsigned char*>(xyz), stride, (int)n, c.pts.p));
+    KLAUNCH_ST(h, c.st, VGICP_PROF_UNPACK, k_unpack_points<<<blocks_for(n, 256), 256, 0, c.st>>>(reinterpret_cast<const unsigned char*>(xyz), stride, (int)n, c.pts.p));
     CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(c.ready, c.st));
     return VGICP_OK;
   }
-  CU_TRY(h, h->staging.reserve(n * stride));
-  CU_TRY(h, cudaMemcpyAsync(h->staging.p, xyz, n * stride, cudaMemcpyHostToDevice, h->stream));
-  KLAUNCH(h, VGICP_PROF_UNPACK, k_unpack_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->staging.p, stride, (int)n, c.pts.p));
+  CU_TRY(h, c.staging.reserve(n * stride));
+  CU_TRY(h, cudaMemcpyAsync(c.staging.p, xyz, n * stride, cudaMemcpyHostToDevice, c.st));
+  // the caller may free/modify xyz after return: pageable copies are staged synchronously by the driver, pinned ones are
+  // not -> wait for the copy itself (an event right behind it), not for the kernels that follow
+  CU_TRY(h, cudaEventRecord(h->ev_copy, c.st));
+  KLAUNCH_ST(h, c.st, VGICP_PROF_UNPACK, k_unpack_points<<<blocks_for(n, 256), 256, 0, c.st>>>(c.staging.p, stride, (int)n, c.pts.p));
   CU_TRY(h, cudaGetLastError());
-  // the caller may free/modify xyz after return: pageable copies are staged synchronously by the driver, pinned ones are not
-  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaEventRecord(c.ready, c.st));
+  CU_TRY(h, cudaEventSynchronize(h->ev_copy));
   return VGICP_OK;
 }
 
@@ -221,8 +237,8 @@ int set_neighbors(vgicp_handle h, Cloud& c, int k, const int* idx, size_t nk) {
   if (!c.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "set_neighbors: cloud not set");
   if (k <= 0 || !idx || nk != (size_t)k * (size_t)c.n) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_neighbors: k * num_points != neighbors.size()");
   CU_TRY(h, c.nbr.reserve(nk));
-  CU_TRY(h, cudaMemcpyAsync(c.nbr.p, idx, nk * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaMemcpyAsync(c.nbr.p, idx, nk * sizeof(int), cudaMemcpyHostToDevice, c.st));
+  CU_TRY(h, cudaStreamSynchronize(c.st));
   c.k = k;
   return VGICP_OK;
 }
@@ -233,16 +249,17 @@ int find_neighbors(vgicp_handle h, Cloud& c, int k) {
   CU_TRY(h, c.nbr.reserve((size_t)c.n * k));
   cudaError_t ke = cudaSuccess;
   if (h->knn_mode == 2) {  // legacy one-thread-per-query scan, kept for A/B measurements
-    KLAUNCH(h, VGICP_PROF_KNN, ke = launch_knn_bruteforce(c.pts.p, c.n, k, c.nbr.p, h->stream));
+    KLAUNCH_ST(h, c.st, VGICP_PROF_KNN, ke = launch_knn_bruteforce(c.pts.p, c.n, k, c.nbr.p, c.st));
   } else {
     const size_t need = knn_grid_scratch_bytes(c.n, nullptr, nullptr);
-    CU_TRY(h, h->knn_scratch.reserve(need));
+    CU_TRY(h, c.knn_scratch.reserve(need));
     int nl = 0;
-    KLAUNCH(h, VGICP_PROF_KNN,
-            ke = launch_knn_grid(c.pts.p, c.n, k, c.nbr.p, h->knn_scratch.p, h->knn_scratch.cap, (h->knn_mode == 1 || c.n < 256) ? 1 : 0, h->exec_hint == 1 ? 2 : 4, &nl, h->stream));
+    KLAUNCH_ST(h, c.st, VGICP_PROF_KNN,
+            ke = launch_knn_grid(c.pts.p, c.n, k, c.nbr.p, c.knn_scratch.p, c.knn_scratch.cap, (h->knn_mode == 1 || c.n < 256) ? 1 : 0, h->exec_hint == 1 ? 2 : 4, &nl, c.st));
     h->launches += nl > 0 ? nl - 1 : 0;
   }
   CU_TRY(h, ke);
+  CU_TRY(h, cudaEventRecord(c.ready, c.st));
   c.k = k;
   return VGICP_OK;
 }
@@ -254,10 +271,11 @@ int calc_covariances(vgicp_handle h, Cloud& c, int method) {
   CU_TRY(h, c.covB.reserve(c.n));
   if (c.n > 0) {
     cudaError_t ke = cudaSuccess;
-    KLAUNCH(h, VGICP_PROF_COVARIANCE, ke = launch_covariance_knn(c.pts.p, c.nbr.p, c.n, c.k, method, c.covA.p, c.covB.p, h->stream));
+    KLAUNCH_ST(h, c.st, VGICP_PROF_COVARIANCE, ke = launch_covariance_knn(c.pts.p, c.nbr.p, c.n, c.k, method, c.covA.p, c.covB.p, c.st));
     CU_TRY(h, ke);
   }
   c.has_cov = true;
+  CU_TRY(h, cudaEventRecord(c.ready, c.st));
   if (method == VGICP_REG_NORMALIZED_MIN_EIG)
     return fail(h, VGICP_ERR_UNSUPPORTED, "unimplemented covariance regularization method was selected (NORMALIZED_MIN_EIG has no GPU path in the reference either); raw covariances kept");
   return VGICP_OK;
@@ -270,10 +288,11 @@ int calc_covariances_rbf(vgicp_handle h, Cloud& c, int method) {
   CU_TRY(h, c.covB.reserve(c.n));
   if (c.n > 0) {
     cudaError_t ke = cudaSuccess;
-    KLAUNCH(h, VGICP_PROF_COVARIANCE, ke = launch_covariance_rbf(c.pts.p, c.n, (float)h->kernel_width, (float)h->kernel_max_dist, method, c.covA.p, c.covB.p, h->stream));
+    KLAUNCH_ST(h, c.st, VGICP_PROF_COVARIANCE, ke = launch_covariance_rbf(c.pts.p, c.n, (float)h->kernel_width, (float)h->kernel_max_dist, method, c.covA.p, c.covB.p, c.st));
     CU_TRY(h, ke);
   }
   c.has_cov = true;
+  CU_TRY(h, cudaEventRecord(c.ready, c.st));
   if (method == VGICP_REG_NORMALIZED_MIN_EIG) return fail(h, VGICP_ERR_UNSUPPORTED, "unimplemented covariance regularization method was selected; raw covariances kept");
   return VGICP_OK;
 }
@@ -284,9 +303,9 @@ int get_covariances(vgicp_handle h, Cloud& c, float* out9, size_t cap) {
   std::vector<float4> a(c.n);
   std::vector<float2> b(c.n);
   if (c.n) {
-    CU_TRY(h, cudaMemcpyAsync(a.data(), c.covA.p, sizeof(float4) * c.n, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(b.data(), c.covB.p, sizeof(float2) * c.n, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaMemcpyAsync(a.data(), c.covA.p, sizeof(float4) * c.n, cudaMemcpyDeviceToHost, c.st));
+    CU_TRY(h, cudaMemcpyAsync(b.data(), c.covB.p, sizeof(float2) * c.n, cudaMemcpyDeviceToHost, c.st));
+    CU_TRY(h, cudaStreamSynchronize(c.st));
   }
   for (int i = 0; i < c.n; i++) {
     float* o = out9 + (size_t)i * 9;
@@ -303,14 +322,35 @@ int get_neighbors(vgicp_handle h, Cloud& c, int* out, size_t cap, int* k_out) {
   size_t need = (size_t)c.n * c.k;
   if (!out || cap < need) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_neighbors: buffer too small");
   if (need) {
-    CU_TRY(h, cudaMemcpyAsync(out, c.nbr.p, need * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaMemcpyAsync(out, c.nbr.p, need * sizeof(int), cudaMemcpyDeviceToHost, c.st));
+    CU_TRY(h, cudaStreamSynchronize(c.st));
   }
   return VGICP_OK;
 }
 
-// GaussianVoxelMap::create_voxelmap(points, covs): gaussian_voxelmap.cu:233-289
-int build_voxelmap(vgicp_handle h) {
+// GaussianVoxelMap::create_voxelmap(points, covs): gaussian_voxelmap.cu:233-289, split in two so that the host does not block
+// on the table-growth decision while the other cloud's work could be enqueued:
+//   voxelmap_begin  enqueues coordinates + the first insertion attempt (8192 buckets) + the read-back of its failure count
+//   voxelmap_finish (called by whoever needs the map) waits for that count, grows the table if the reference would
+//                   (:265-285), then ids / accumulate / finalize.  num_voxels itself is fetched lazily.
+int voxelmap_attempt(vgicp_handle h, int B) {
+  Cloud& t = h->target;
+  VoxelMap& m = h->map;
+  const int n = t.n;
+  CU_TRY(h, m.slots.reserve(B));
+  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_fill_i32<<<blocks_for(B, 256), 256, 0, t.st>>>(m.slots.p, -1, (size_t)B));
+  CU_TRY(h, cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(int), t.st));
+  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_table_insert<<<blocks_for(n, 256), 256, 0, t.st>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan));
+  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP,
+             k_table_lookup_points<<<blocks_for(n, 256), 256, 0, t.st>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan, m.slot_of_point.p, h->d_counters));
+  CU_TRY(h, cudaGetLastError());
+  CU_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int), cudaMemcpyDeviceToHost, t.st));
+  CU_TRY(h, cudaEventRecord(m.ev_attempt, t.st));
+  m.pending_B = B;
+  return VGICP_OK;
+}
+
+int voxelmap_begin(vgicp_handle h) {
   Cloud& t = h->target;
   VoxelMap& m = h->map;
   if (!t.has_pts || !t.has_cov) return fail(h, VGICP_ERR_BAD_STATE, "create_target_voxelmap: target points and covariances required");
@@ -320,43 +360,75 @@ int build_voxelmap(vgicp_handle h) {
     m.res = (float)h->resolution;
   }
   m.built = false;
+  m.pending = false;
   const int n = t.n;
   CU_TRY(h, m.coords.reserve(n));
   CU_TRY(h, m.slot_of_point.reserve(n));
-  KLAUNCH(h, VGICP_PROF_VOXELMAP, k_voxel_coords<<<blocks_for(n, 256), 256, 0, h->stream>>>(t.pts.p, n, m.res, m.coords.p));
-  int B = m.init_num_buckets;
-  for (;; B *= 2) {  // :265 (no upper bound in the reference; bounded here)
-    if (B > (1 << 28)) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "create_target_voxelmap: hash table would exceed 2^28 buckets");
-    CU_TRY(h, m.slots.reserve(B));
-    KLAUNCH(h, VGICP_PROF_VOXELMAP, k_fill_i32<<<blocks_for(B, 256), 256, 0, h->stream>>>(m.slots.p, -1, (size_t)B));
-    CU_TRY(h, cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(int), h->stream));
-    KLAUNCH(h, VGICP_PROF_VOXELMAP, k_table_insert<<<blocks_for(n, 256), 256, 0, h->stream>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan));
-    KLAUNCH(h, VGICP_PROF_VOXELMAP,
-            k_table_lookup_points<<<blocks_for(n, 256), 256, 0, h->stream>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan, m.slot_of_point.p, h->d_counters));
-    CU_TRY(h, cudaGetLastError());
-    CU_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_coords<<<blocks_for(n, 256), 256, 0, t.st>>>(t.pts.p, n, m.res, m.coords.p));
+  int rc = voxelmap_attempt(h, m.init_num_buckets);
+  if (rc) return rc;
+  m.pending = true;
+  return VGICP_OK;
+}
+
+int voxelmap_finish(vgicp_handle h) {
+  Cloud& t = h->target;
+  VoxelMap& m = h->map;
+  if (!m.pending) return m.built ? VGICP_OK : fail(h, VGICP_ERR_BAD_STATE, "target voxel map not built");
+  const int n = t.n;
+  int B = m.pending_B;
+  for (;;) {  // :265 (no upper bound in the reference; bounded here)
+    CU_TRY(h, cudaEventSynchronize(m.ev_attempt));
     if ((double)h->h_counters[0] / (double)n < 0.01) break;  // :280
+    B *= 2;
+    if (B > (1 << 28)) { m.pending = false; return fail(h, VGICP_ERR_INVALID_ARGUMENT, "create_target_voxelmap: hash table would exceed 2^28 buckets"); }
+    int rc = voxelmap_attempt(h, B);
+    if (rc) return rc;
   }
+  m.pending = false;
   m.num_buckets = B;
+  const int vmax = n < B ? n : B;  // upper bound on the number of voxels: buffers are sized for it, the exact count arrives later
   CU_TRY(h, m.buckets.reserve(B));
-  KLAUNCH(h, VGICP_PROF_VOXELMAP, k_table_assign_ids<<<1, 1024, 0, h->stream>>>(m.coords.p, m.slots.p, B, m.buckets.p, h->d_counters + 1));
-  CU_TRY(h, cudaMemcpyAsync(h->h_counters + 1, h->d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  CU_TRY(h, cudaStreamSynchronize(h->stream));
-  const int V = h->h_counters[1];
-  m.num_voxels = V;
-  CU_TRY(h, m.vox.reserve(V > 0 ? V : 1));
-  CU_TRY(h, m.sums.reserve((size_t)(V > 0 ? V : 1) * 10));
-  CU_TRY(h, m.counts.reserve(V > 0 ? V : 1));
-  if (V > 0) {
-    CU_TRY(h, cudaMemsetAsync(m.sums.p, 0, sizeof(double) * 10 * (size_t)V, h->stream));
-    CU_TRY(h, cudaMemsetAsync(m.counts.p, 0, sizeof(int) * (size_t)V, h->stream));
-    KLAUNCH(h, VGICP_PROF_VOXELMAP,
-            k_voxel_accumulate<<<blocks_for(n, 256), 256, 0, h->stream>>>(t.pts.p, t.covA.p, t.covB.p, n, m.slot_of_point.p, m.buckets.p, m.sums.p, m.counts.p));
-    KLAUNCH(h, VGICP_PROF_VOXELMAP, k_voxel_finalize<<<blocks_for(V, 256), 256, 0, h->stream>>>(m.sums.p, m.counts.p, V, m.vox.p));
-    CU_TRY(h, cudaGetLastError());
-  }
+  CU_TRY(h, m.vox.reserve(vmax));
+  CU_TRY(h, m.sums.reserve((size_t)vmax * 10));
+  CU_TRY(h, m.counts.reserve(vmax));
+  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_table_assign_ids<<<1, 1024, 0, t.st>>>(m.coords.p, m.slots.p, B, m.buckets.p, h->d_counters + 1));
+  CU_TRY(h, cudaMemsetAsync(m.sums.p, 0, sizeof(double) * 10 * (size_t)vmax, t.st));
+  CU_TRY(h, cudaMemsetAsync(m.counts.p, 0, sizeof(int) * (size_t)vmax, t.st));
+  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP,
+             k_voxel_accumulate<<<blocks_for(n, 256), 256, 0, t.st>>>(t.pts.p, t.covA.p, t.covB.p, n, m.slot_of_point.p, m.buckets.p, m.sums.p, m.counts.p));
+  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_finalize<<<blocks_for(vmax, 256), 256, 0, t.st>>>(m.sums.p, m.counts.p, h->d_counters + 1, m.vox.p));
+  CU_TRY(h, cudaGetLastError());
+  CU_TRY(h, cudaMemcpyAsync(h->h_counters + 1, h->d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, t.st));
+  CU_TRY(h, cudaEventRecord(m.ev_done, t.st));
+  CU_TRY(h, cudaEventRecord(t.ready, t.st));
+  m.v_pending = true;
   m.built = true;
+  return VGICP_OK;
+}
+
+int voxelmap_num_voxels(vgicp_handle h, int* nv) {
+  int rc = voxelmap_finish(h);
+  if (rc) return rc;
+  VoxelMap& m = h->map;
+  if (m.v_pending) {
+    CU_TRY(h, cudaEventSynchronize(m.ev_done));
+    m.num_voxels = h->h_counters[1];
+    m.v_pending = false;
+  }
+  *nv = m.num_voxels;
+  return VGICP_OK;
+}
+
+int build_voxelmap(vgicp_handle h) { return voxelmap_begin(h); }
+
+// everything an evaluation on the main stream depends on: the finished voxel map and the last operations enqueued on the two
+// cloud streams
+int sync_inputs(vgicp_handle h) {
+  int rc = voxelmap_finish(h);
+  if (rc) return rc;
+  if (h->target.st != h->stream && h->target.ready) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->target.ready, 0));
+  if (h->source.st != h->stream && h->source.ready) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->source.ready, 0));
   return VGICP_OK;
 }
 
@@ -416,7 +488,7 @@ int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H) {
     else if (G == 4) LAUNCH_LIN_G(MODE, 4); \
     else LAUNCH_LIN_G(MODE, 1);          \
   } while (0)
-  prof_begin(h, want_H ? VGICP_PROF_LINEARIZE : VGICP_PROF_ERROR);
+  prof_begin(h, want_H ? VGICP_PROF_LINEARIZE : VGICP_PROF_ERROR, h->stream);
   switch (h->offset_mode) {
     case 1: LAUNCH_LIN_G(1, 1); break;
     case 7: LAUNCH_LIN(7); break;
@@ -425,7 +497,7 @@ int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H) {
   }
 #undef LAUNCH_LIN_G
 #undef LAUNCH_LIN
-  prof_end(h);
+  prof_end(h, h->stream);
   h->launches++;
   CU_TRY(h, cudaGetLastError());
   return VGICP_OK;
@@ -442,7 +514,7 @@ int launch_lm_step(vgicp_handle h, const LinLaunch& L) {
     else if (G == 4) LAUNCH_LM_G(MODE, 4); \
     else LAUNCH_LM_G(MODE, 1);          \
   } while (0)
-  prof_begin(h, VGICP_PROF_LINEARIZE);
+  prof_begin(h, VGICP_PROF_LINEARIZE, h->stream);
   switch (h->offset_mode) {
     case 1: LAUNCH_LM_G(1, 1); break;
     case 7: LAUNCH_LM(7); break;
@@ -451,7 +523,7 @@ int launch_lm_step(vgicp_handle h, const LinLaunch& L) {
   }
 #undef LAUNCH_LM_G
 #undef LAUNCH_LM
-  prof_end(h);
+  prof_end(h, h->stream);
   h->launches++;
   CU_TRY(h, cudaGetLastError());
   return VGICP_OK;
@@ -459,7 +531,7 @@ int launch_lm_step(vgicp_handle h, const LinLaunch& L) {
 
 int check_ready_for_eval(vgicp_handle h, const char* who) {
   if (!h->source.has_pts || !h->source.has_cov) return fail(h, VGICP_ERR_BAD_STATE, std::string(who) + ": source points and covariances required");
-  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, std::string(who) + ": target voxel map not built");
+  if (!h->map.built && !h->map.pending) return fail(h, VGICP_ERR_BAD_STATE, std::string(who) + ": target voxel map not built");
   if (!h->has_lin) return fail(h, VGICP_ERR_BAD_STATE, std::string(who) + ": update_correspondences has not been called");
   return VGICP_OK;
 }
@@ -503,6 +575,14 @@ int vgicp_create(int device, vgicp_handle* out) {
     return VGICP_ERR_NO_DEVICE;
   }
   bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&h->stream_b, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->target.ready, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->source.ready, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->map.ev_attempt, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->map.ev_done, cudaEventDisableTiming) == cudaSuccess;
+  h->target.st = h->stream;    // the target (and its voxel map) is built on the main stream, where the evaluations run
+  h->source.st = h->stream_b;  // the source's stage 1 overlaps with it
   ok = ok && cudaMalloc(&h->d_ticket, sizeof(unsigned int)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->d_counters, 4 * sizeof(int)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->d_out, 64 * sizeof(double)) == cudaSuccess;
@@ -527,12 +607,12 @@ int vgicp_destroy(vgicp_handle h) {
   if (!h) return VGICP_OK;
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream_b) cudaStreamSynchronize(h->stream_b);
   h->source.release();
   h->target.release();
   h->map.release();
   h->d_offsets.release();
   h->staging.release();
-  h->knn_scratch.release();
   if (h->comm_ranks > 1) vgicp_comm_shutdown(h);
   if (h->comm_box) cudaFree(h->comm_box);
   h->partials.release();
@@ -546,6 +626,9 @@ int vgicp_destroy(vgicp_handle h) {
   if (h->h_lm) cudaFreeHost(h->h_lm);
   for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->prof_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : {h->ev_copy, h->target.ready, h->source.ready, h->map.ev_attempt, h->map.ev_done})
+    if (e) cudaEventDestroy(e);
+  if (h->stream_b) cudaStreamDestroy(h->stream_b);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return VGICP_OK;
@@ -626,14 +709,20 @@ int vgicp_set_target_cloud(vgicp_handle h, const float* xyz, size_t n, size_t st
   h->target.k = 0;
   h->target.has_cov = false;
   h->map.built = false;
+  h->map.pending = false;
   return set_cloud(h, h->target, xyz, n, stride_bytes);
 }
 
 int vgicp_swap_source_and_target(vgicp_handle h) {  // fast_vgicp_cuda.cu:97-107
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
+  // the clouds keep their streams; everything in flight (incl. a pending map build that reads the old target) must land first
+  if (h->map.pending) { int rc0 = voxelmap_finish(h); if (rc0) return rc0; }
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream_b));
   std::swap(h->source, h->target);
   h->map.built = false;
+  h->map.pending = false;
   if (!h->target.has_pts || !h->target.has_cov) return VGICP_OK;
   return build_voxelmap(h);
 }
@@ -720,24 +809,26 @@ int vgicp_create_target_voxelmap(vgicp_handle h) {
 int vgicp_get_num_voxels(vgicp_handle h, int* nv) {
   CHECK_HANDLE(h);
   if (!nv) return VGICP_ERR_INVALID_ARGUMENT;
-  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "voxel map not built");
-  *nv = h->map.num_voxels;
-  return VGICP_OK;
+  DeviceGuard g(h->device);
+  return voxelmap_num_voxels(h, nv);
 }
 int vgicp_get_num_buckets(vgicp_handle h, int* nb) {
   CHECK_HANDLE(h);
   if (!nb) return VGICP_ERR_INVALID_ARGUMENT;
-  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "voxel map not built");
+  DeviceGuard g(h->device);
+  { int rc = voxelmap_finish(h); if (rc) return rc; }
   *nb = h->map.num_buckets;
   return VGICP_OK;
 }
 
 static int fetch_voxels(vgicp_handle h, std::vector<VoxelRec>& v) {
-  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "voxel map not built");
-  v.resize(h->map.num_voxels);
+  int nv = 0;
+  int rc = voxelmap_num_voxels(h, &nv);
+  if (rc) return rc;
+  v.resize(nv);
   if (!v.empty()) {
-    CU_TRY(h, cudaMemcpyAsync(v.data(), h->map.vox.p, sizeof(VoxelRec) * v.size(), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaMemcpyAsync(v.data(), h->map.vox.p, sizeof(VoxelRec) * v.size(), cudaMemcpyDeviceToHost, h->target.st));
+    CU_TRY(h, cudaStreamSynchronize(h->target.st));
   }
   return VGICP_OK;
 }
@@ -781,12 +872,12 @@ int vgicp_get_voxel_covs(vgicp_handle h, float* out9, size_t cap) {
 int vgicp_get_voxel_buckets(vgicp_handle h, int* coords3, int* ids, size_t cap) {
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
-  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "voxel map not built");
+  { int rc = voxelmap_finish(h); if (rc) return rc; }
   size_t B = (size_t)h->map.num_buckets;
   if (cap < B || !coords3 || !ids) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_voxel_buckets: buffer too small");
   std::vector<int4> b(B);
-  CU_TRY(h, cudaMemcpyAsync(b.data(), h->map.buckets.p, sizeof(int4) * B, cudaMemcpyDeviceToHost, h->stream));
-  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaMemcpyAsync(b.data(), h->map.buckets.p, sizeof(int4) * B, cudaMemcpyDeviceToHost, h->target.st));
+  CU_TRY(h, cudaStreamSynchronize(h->target.st));
   for (size_t i = 0; i < B; i++) {
     coords3[3 * i] = b[i].x; coords3[3 * i + 1] = b[i].y; coords3[3 * i + 2] = b[i].z;
     ids[i] = b[i].w;
@@ -798,7 +889,7 @@ int vgicp_update_correspondences(vgicp_handle h, const double T[16]) {  // fast_
   CHECK_HANDLE(h);
   if (!T) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "update_correspondences: null pose");
   if (!h->source.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "update_correspondences: source cloud not set");
-  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "update_correspondences: target voxel map not built");
+  if (!h->map.built && !h->map.pending) return fail(h, VGICP_ERR_BAD_STATE, "update_correspondences: target voxel map not built");
   h->lin = to_pose(T);  // linearized_x = trans.cast<float>()
   h->has_lin = true;
   // the lookup itself is fused into the evaluation kernel; the explicit list is only built by the getter
@@ -808,7 +899,9 @@ int vgicp_update_correspondences(vgicp_handle h, const double T[16]) {  // fast_
 int vgicp_get_voxel_correspondences(vgicp_handle h, int* pairs, size_t cap, size_t* n_pairs) {
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
-  if (!h->source.has_pts || !h->map.built || !h->has_lin) return fail(h, VGICP_ERR_BAD_STATE, "get_voxel_correspondences: update_correspondences has not been called");
+  if (!h->source.has_pts || (!h->map.built && !h->map.pending) || !h->has_lin)
+    return fail(h, VGICP_ERR_BAD_STATE, "get_voxel_correspondences: update_correspondences has not been called");
+  { int rc = sync_inputs(h); if (rc) return rc; }
   const int n = h->source.n;
   const int n_off = (int)h->h_offsets.size();
   size_t total = (size_t)n * n_off;
@@ -841,6 +934,7 @@ int vgicp_compute_error(vgicp_handle h, const double T[16], double* H36, double*
   if (!T) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "compute_error: null pose");
   int rc = check_ready_for_eval(h, "compute_error");
   if (rc) return rc;
+  if ((rc = sync_inputs(h))) return rc;
   return evaluate(h, T, H36, b6, err);
 }
 
@@ -863,7 +957,8 @@ int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* 
   vgicp_lsq_params P;
   if (params) P = *params; else vgicp_lsq_default_params(&P);
   if (!h->source.has_pts || !h->source.has_cov) return fail(h, VGICP_ERR_BAD_STATE, "align: source points and covariances required");
-  if (!h->map.built) return fail(h, VGICP_ERR_BAD_STATE, "align: target voxel map not built");
+  if (!h->map.built && !h->map.pending) return fail(h, VGICP_ERR_BAD_STATE, "align: target voxel map not built");
+  { int rc = sync_inputs(h); if (rc) return rc; }
 
   if (h->align_mode == 0 && h->comm_ranks <= 1) {
     // device-resident loop: initialise the state block, enqueue evaluation links, read the state back once per chunk
@@ -979,7 +1074,7 @@ int vgicp_register(vgicp_handle h, const float* target_xyz, size_t n_target, con
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
   int rc;
-  h->target.k = 0; h->target.has_cov = false; h->map.built = false;
+  h->target.k = 0; h->target.has_cov = false; h->map.built = false; h->map.pending = false;
   if ((rc = set_cloud(h, h->target, target_xyz, n_target, stride_bytes, on_device != 0))) return rc;
   if ((rc = find_neighbors(h, h->target, k))) return rc;
   if ((rc = calc_covariances(h, h->target, regularization_method))) return rc;
@@ -1000,6 +1095,7 @@ int vgicp_transform_source(vgicp_handle h, const double T[16], float* out_xyz, s
   const int n = h->source.n;
   if (cap < (size_t)n || stride < 12 || stride % 4) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "transform_source: bad capacity/stride");
   if (n == 0) return VGICP_OK;
+  if (h->source.st != h->stream) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->source.ready, 0));
   CU_TRY(h, h->staging.reserve((size_t)n * stride));
   // keep the non-xyz bytes of the caller's records untouched: copy in, overwrite xyz, copy out
   if (stride > 12) CU_TRY(h, cudaMemcpyAsync(h->staging.p, out_xyz, (size_t)n * stride, cudaMemcpyHostToDevice, h->stream));
@@ -1024,6 +1120,7 @@ int vgicp_set_target_cloud_device(vgicp_handle h, const float* d_xyz, size_t n, 
   h->target.k = 0;
   h->target.has_cov = false;
   h->map.built = false;
+  h->map.pending = false;
   return set_cloud(h, h->target, d_xyz, n, stride_bytes, true);
 }
 
@@ -1127,6 +1224,7 @@ int vgicp_set_knn_mode(vgicp_handle h, int mode) {
 int vgicp_set_profiling(vgicp_handle h, int enable) {
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
+  CU_TRY(h, cudaStreamSynchronize(h->stream_b));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   for (auto& r : h->prof_pending) { h->prof_pool.push_back(r.a); h->prof_pool.push_back(r.b); }
   h->prof_pending.clear();
@@ -1139,6 +1237,7 @@ int vgicp_get_profile(vgicp_handle h, double* ms, uint64_t* launches, int capaci
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
   if (!ms || !launches || capacity < VGICP_PROF_NUM_CATEGORIES) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_profile: need VGICP_PROF_NUM_CATEGORIES entries");
+  CU_TRY(h, cudaStreamSynchronize(h->stream_b));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   for (auto& r : h->prof_pending) {
     float t = 0.f;
@@ -1166,6 +1265,8 @@ int vgicp_get_fitness_score(vgicp_handle h, const double T[16], double max_range
   const int n = h->source.n;
   *score = std::numeric_limits<double>::max();
   if (n == 0 || h->target.n == 0) return VGICP_OK;
+  if (h->source.st != h->stream) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->source.ready, 0));
+  if (h->target.st != h->stream) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->target.ready, 0));
   CU_TRY(h, h->staging.reserve((size_t)n * sizeof(float)));
   float* d_out = reinterpret_cast<float*>(h->staging.p);
   KLAUNCH(h, VGICP_PROF_OTHER, k_nn1_sqdist<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->source.pts.p, n, h->target.pts.p, h->target.n, to_pose(T), d_out));
@@ -1191,6 +1292,8 @@ int vgicp_get_launch_count(vgicp_handle h, uint64_t* launches) {
 int vgicp_synchronize(vgicp_handle h) {
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
+  if (h->map.pending) { int rc = voxelmap_finish(h); if (rc) return rc; }
+  CU_TRY(h, cudaStreamSynchronize(h->stream_b));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   return VGICP_OK;
 }

@@ -238,9 +238,9 @@ __global__ void k_voxel_accumulate(const float4* __restrict__ pts, const float4*
   atomicAdd(d + 6, (double)a.w); atomicAdd(d + 7, (double)b.x); atomicAdd(d + 8, (double)b.y);
 }
 
-__global__ void k_voxel_finalize(const double* __restrict__ sums, const int* __restrict__ counts, int nv, VoxelRec* __restrict__ vox) {  // :158-176
+__global__ void k_voxel_finalize(const double* __restrict__ sums, const int* __restrict__ counts, const int* __restrict__ nv_ptr, VoxelRec* __restrict__ vox) {  // :158-176
   int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= nv) return;
+  if (v >= *nv_ptr) return;  // launched for an upper bound; the voxel count is still on the device
   int c = counts[v];
   double inv = 1.0 / (double)c;
   const double* d = sums + (size_t)v * 10;
