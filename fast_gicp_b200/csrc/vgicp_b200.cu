@@ -125,7 +125,9 @@ struct vgicp_context {
   unsigned int* d_ticket = nullptr;
   int* d_counters = nullptr;  // [0] fail count, [1] num_voxels
   double* d_out = nullptr;    // 43 doubles
-  double* h_out = nullptr;    // pinned
+  double* h_out = nullptr;    // pinned + mapped: in latency mode the kernel's last block writes the result straight here
+  unsigned long long* h_flag = nullptr;  // pinned + mapped completion word
+  unsigned long long eval_seq = 0;
   int* h_counters = nullptr;  // pinned
 
   // optional per-kernel timing (vgicp_set_profiling): CUDA events on the handle's stream around every launch
@@ -452,6 +454,7 @@ LinLaunch make_lin_launch(vgicp_handle h) {
   a.offsets = h->d_offsets.p; a.n_off = (int)h->h_offsets.size(); a.res = m.res;
   a.Tlin = h->lin; a.Teval = h->lin;
   a.partials = h->partials.p; a.ticket = h->d_ticket; a.out = h->d_out;
+  a.done_flag = nullptr; a.done_seq = 0;
   // lanes per source point: split the neighbour cells of a point over G lanes while the cloud is too small to fill the
   // GPU with one thread per point (latency-bound regime); one lane per point once it is large (ALU/bandwidth-bound regime)
   const int n_off = a.n_off;
@@ -471,11 +474,16 @@ LinLaunch make_lin_launch(vgicp_handle h) {
 }
 
 // one evaluation: launches the fused lookup+derivative kernel; result lands in h->h_out after the stream sync
-int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H) {
+int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H, bool direct_to_host = false) {
   LinLaunch L = make_lin_launch(h);
   LinArgs& a = L.a;
   a.Teval = Teval;
   a.comm_seq = h->comm_seq++;
+  if (direct_to_host) {  // UVA: the mapped pinned pointers are valid on the device
+    a.out = h->h_out;
+    a.done_flag = h->h_flag;
+    a.done_seq = ++h->eval_seq;
+  }
   const int grid = L.grid, G = L.G;
 #define LAUNCH_LIN_G(MODE, GG)                                                           \
   do {                                                                                   \
@@ -538,10 +546,26 @@ int check_ready_for_eval(vgicp_handle h, const char* who) {
 
 int evaluate(vgicp_handle h, const double* T, double* H36, double* b6, double* err) {
   const bool want_H = (H36 != nullptr && b6 != nullptr);  // compute_derivatives.cu:160
-  int rc = launch_linearize(h, to_pose(T), want_H);
+  const bool direct = h->exec_hint == 0;  // latency mode: result written to mapped host memory, host spins on a flag
+  int rc = launch_linearize(h, to_pose(T), want_H, direct);
   if (rc) return rc;
-  CU_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * (want_H ? 43 : 1), cudaMemcpyDeviceToHost, h->stream));
-  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (direct) {
+    const unsigned long long want = h->eval_seq;
+    volatile unsigned long long* flag = h->h_flag;
+    long spins = 0;
+    while (*flag != want) {
+      __builtin_ia32_pause();
+      if (++spins > 2000000L) {  // ~a few ms without an answer: fall back to a blocking wait (also surfaces launch errors)
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        if (*flag != want) return fail(h, VGICP_ERR_CUDA, "evaluate: kernel finished without publishing its result");
+        break;
+      }
+    }
+    __sync_synchronize();
+  } else {
+    CU_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * (want_H ? 43 : 1), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
   if (err) *err = h->h_out[0];
   if (want_H) {
     memcpy(H36, h->h_out + 1, 36 * sizeof(double));
@@ -586,7 +610,9 @@ int vgicp_create(int device, vgicp_handle* out) {
   ok = ok && cudaMalloc(&h->d_ticket, sizeof(unsigned int)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->d_counters, 4 * sizeof(int)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->d_out, 64 * sizeof(double)) == cudaSuccess;
-  ok = ok && cudaMallocHost(&h->h_out, 64 * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaHostAlloc(&h->h_out, 64 * sizeof(double), cudaHostAllocMapped) == cudaSuccess;
+  ok = ok && cudaHostAlloc(&h->h_flag, 64, cudaHostAllocMapped) == cudaSuccess;
+  if (ok) *h->h_flag = 0;
   ok = ok && cudaMallocHost(&h->h_counters, 4 * sizeof(int)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->d_lm, sizeof(LmState)) == cudaSuccess;
   ok = ok && cudaMallocHost(&h->h_lm, sizeof(LmState)) == cudaSuccess;
@@ -621,6 +647,7 @@ int vgicp_destroy(vgicp_handle h) {
   if (h->d_counters) cudaFree(h->d_counters);
   if (h->d_out) cudaFree(h->d_out);
   if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->h_flag) cudaFreeHost(h->h_flag);
   if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->d_lm) cudaFree(h->d_lm);
   if (h->h_lm) cudaFreeHost(h->h_lm);

@@ -274,7 +274,9 @@ struct LinArgs {
   Pose Tlin, Teval;
   double* partials;       // [gridDim.x][kLinValues]
   unsigned int* ticket;   // zero before first launch; reset by the last block
-  double* out;            // [43]: err, H (36, column-major), b (6)
+  double* out;            // [43]: err, H (36, column-major), b (6); may be mapped pinned host memory
+  volatile unsigned long long* done_flag;  // optional (mapped host memory): set to done_seq once `out` is complete
+  unsigned long long done_seq;
   // source sharded over several GPUs: the folded sums of this rank are exchanged with the peers by the last
   // block itself, through mailboxes in peer memory (NVLink P2P stores), and summed in rank order
   int comm_ranks;         // 0/1 = single GPU
@@ -605,6 +607,10 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
   if (threadIdx.x == 0) {
     lin_unpack<WANT_H>(fin[0], a.out);
     *a.ticket = 0u;
+    if (a.done_flag) {  // the host spins on this word instead of waiting for the stream (saves the copy + wake-up latency)
+      __threadfence_system();
+      *a.done_flag = a.done_seq;
+    }
   }
 }
 
