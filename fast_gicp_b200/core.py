@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvgicp_b200.so")
+LIB_PATH = os.environ.get("VGICP_B200_LIB") or os.path.join(_HERE, "lib", "libvgicp_b200.so")  # override only for A/B experiments
 
 OK, ERR_INVALID_ARGUMENT, ERR_BAD_STATE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_COMM = range(7)
 
