@@ -8,6 +8,8 @@ from .registration import (  # noqa: F401
     FastVGICPCuda,
     LsqRegistration,
     LSQ_OPTIMIZER_TYPE,
+    NDTCuda,
+    NDTDistanceMode,
     NearestNeighborMethod,
     NeighborSearchMethod,
     RegularizationMethod,

@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "vgicp_lsq_default_params", "vgicp_align", "vgicp_transform_source",
     "vgicp_get_launch_count", "vgicp_synchronize", "vgicp_get_stream",
     "vgicp_set_source_cloud_device", "vgicp_set_target_cloud_device", "vgicp_set_profiling", "vgicp_get_profile", "vgicp_profile_category_name",
-    "vgicp_set_knn_mode", "vgicp_register", "vgicp_set_align_mode", "vgicp_get_fitness_score", "vgicp_set_execution_hint",
+    "vgicp_set_knn_mode", "vgicp_register", "vgicp_set_align_mode", "vgicp_get_fitness_score", "vgicp_set_execution_hint", "vgicp_set_problem", "vgicp_ndt_create_voxelmaps",
     "vgicp_comm_export", "vgicp_comm_init", "vgicp_comm_shutdown", "vgicp_comm_error", "vgicp_set_source_shard", "vgicp_clear_source_shard",
 ]
 PROF_NUM_CATEGORIES = 7
@@ -128,6 +128,8 @@ def load_library():
         "vgicp_set_align_mode": [hp, C.c_int],
         "vgicp_get_fitness_score": [hp, dp, C.c_double, dp],
         "vgicp_set_execution_hint": [hp, C.c_int],
+        "vgicp_set_problem": [hp, C.c_int],
+        "vgicp_ndt_create_voxelmaps": [hp],
         "vgicp_comm_export": [hp, C.c_void_p],
         "vgicp_comm_init": [hp, C.c_int, C.c_int, C.c_void_p],
         "vgicp_comm_shutdown": [hp],
@@ -237,6 +239,13 @@ class Core:
         """Points already resident in this GPU's memory (e.g. a torch CUDA tensor's data_ptr())."""
         fn = self._lib.vgicp_set_source_cloud_device if which == "source" else self._lib.vgicp_set_target_cloud_device
         self._check(fn(self._h, dev_ptr, n, stride))
+
+    def set_problem(self, problem):
+        """0 = VGICP (default), 1 = NDT P2D, 2 = NDT D2D."""
+        self._check(self._lib.vgicp_set_problem(self._h, int(problem)))
+
+    def ndt_create_voxelmaps(self):
+        self._check(self._lib.vgicp_ndt_create_voxelmaps(self._h))
 
     def set_execution_hint(self, hint):
         """0 = latency (default), 1 = throughput (many handles share the GPU)."""

@@ -10,11 +10,13 @@
 #include <unordered_map>
 
 #include <fast_gicp_b200/fast_vgicp_cuda.hpp>
+#include <fast_gicp_b200/ndt_cuda.hpp>
 
 namespace py = pybind11;
 using Cloud = pcl::PointCloud<pcl::PointXYZ>;
 using LsqReg = fast_gicp::LsqRegistration<pcl::PointXYZ, pcl::PointXYZ>;
 using VgicpCuda = fast_gicp::FastVGICPCuda<pcl::PointXYZ, pcl::PointXYZ>;
+using NdtCuda = fast_gicp::NDTCuda<pcl::PointXYZ, pcl::PointXYZ>;
 using ArrD = py::array_t<double, py::array::c_style | py::array::forcecast>;
 using ArrF = py::array_t<float, py::array::c_style | py::array::forcecast>;
 
@@ -102,9 +104,22 @@ static py::array_t<double> align_points(const ArrD& target, const ArrD& source, 
     target_cloud = approximate_voxel_grid(*target_cloud, static_cast<float>(downsample_resolution));
     source_cloud = approximate_voxel_grid(*source_cloud, static_cast<float>(downsample_resolution));
   }
+  if (method == "NDT_CUDA") {  // main.cpp:125-133
+    NdtCuda ndt;
+    ndt.setResolution(voxel_resolution);
+    ndt.setNeighborSearchMethod(search_method(neighbor_search_method), neighbor_search_radius);
+    ndt.setInputTarget(target_cloud);
+    ndt.setInputSource(source_cloud);
+    Cloud aligned;
+    {
+      py::gil_scoped_release release;
+      ndt.align(aligned, to_mat4f(initial_guess));
+    }
+    return to_numpy(ndt.getFinalTransformation().cast<double>());
+  }
   if (method != "VGICP_CUDA") {
-    if (method == "GICP" || method == "VGICP" || method == "NDT_CUDA")
-      std::cerr << "error: this build provides only VGICP_CUDA (the B200 path); " << method << " is outside it" << std::endl;
+    if (method == "GICP" || method == "VGICP")
+      std::cerr << "error: this build provides only VGICP_CUDA and NDT_CUDA (the B200 paths); " << method << " is outside it" << std::endl;
     else
       std::cerr << "error: unknown registration method " << method << std::endl;
     return to_numpy(Eigen::Matrix4d::Identity());
@@ -164,6 +179,13 @@ PYBIND11_MODULE(pygicp, m) {
            return score;
          },
          py::arg("max_range") = std::numeric_limits<double>::max());
+
+  py::class_<NdtCuda, LsqReg, std::shared_ptr<NdtCuda>>(m, "NDTCuda")  // main.cpp:204-212
+    .def(py::init([]() { return std::make_shared<NdtCuda>(0); }))
+    .def("set_neighbor_search_method", [](NdtCuda& v, const std::string& method, double radius) { v.setNeighborSearchMethod(search_method(method), radius); },
+         py::arg("method") = "DIRECT1", py::arg("radius") = 1.5)
+    .def("set_resolution", &NdtCuda::setResolution)
+    .def("set_distance_mode", [](NdtCuda& v, const std::string& mode) { v.setDistanceMode(mode == "P2D" ? fast_gicp::NDTDistanceMode::P2D : fast_gicp::NDTDistanceMode::D2D); });
 
   m.attr("__version__") = "b200-dev";
 }

@@ -69,6 +69,9 @@ struct VoxelMap {
   int pending_B = 0;
   bool v_pending = false;  // num_voxels still in flight
   cudaEvent_t ev_attempt = nullptr, ev_done = nullptr;
+  int ndt = 0;             // 1: built from the points alone + MIN_EIG (NDT), 0: from points + covariances (VGICP)
+  int* d_counters = nullptr;  // [0] fail count, [1] num_voxels
+  int* h_counters = nullptr;  // pinned
   float res = 1.0f;
   int init_num_buckets = 8192;  // gaussian_voxelmap.cuh:20
   int max_scan = 10;            // gaussian_voxelmap.cuh:20
@@ -123,12 +126,19 @@ struct vgicp_context {
   DevBuf<double> partials;
   DevBuf<int> corr_ids;
   unsigned int* d_ticket = nullptr;
-  int* d_counters = nullptr;  // [0] fail count, [1] num_voxels
   double* d_out = nullptr;    // 43 doubles
   double* h_out = nullptr;    // pinned + mapped: in latency mode the kernel's last block writes the result straight here
   unsigned long long* h_flag = nullptr;  // pinned + mapped completion word
   unsigned long long eval_seq = 0;
-  int* h_counters = nullptr;  // pinned
+
+  // NDT (NDTCudaCore, ndt_cuda.cu): 0 = VGICP problem, 1 = NDT point-to-distribution, 2 = NDT distribution-to-distribution
+  int problem = 0;
+  VoxelMap ndt_t, ndt_s;        // target / source NDT voxel maps
+  DevBuf<float4> ndt_src_pts;   // D2D: source voxel means as the evaluation's source cloud
+  DevBuf<float4> ndt_src_covA;  // D2D: source voxel covariances; P2D: zeros
+  DevBuf<float2> ndt_src_covB;
+  int ndt_src_n = 0;
+  bool ndt_ready = false;
 
   // optional per-kernel timing (vgicp_set_profiling): CUDA events on the handle's stream around every launch
   bool prof_on = false;
@@ -210,6 +220,7 @@ Pose to_pose(const double* T) {  // Eigen::Isometry3d (column-major) -> float im
 }
 
 int set_cloud(vgicp_handle h, Cloud& c, const float* xyz, size_t n, size_t stride, bool on_device = false) {
+  h->ndt_ready = false;  // NDT voxel maps are rebuilt lazily from the new points (ndt_cuda.cu:104,114 reset the maps)
   if (n > 0 && !xyz) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_cloud: null points");
   if (stride < 12 || (stride % 4) != 0) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_cloud: stride_bytes must be a multiple of 4 and >= 12");
   if (n > (size_t)0x7fffffff / 64) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_cloud: too many points");
@@ -335,27 +346,23 @@ int get_neighbors(vgicp_handle h, Cloud& c, int* out, size_t cap, int* k_out) {
 //   voxelmap_begin  enqueues coordinates + the first insertion attempt (8192 buckets) + the read-back of its failure count
 //   voxelmap_finish (called by whoever needs the map) waits for that count, grows the table if the reference would
 //                   (:265-285), then ids / accumulate / finalize.  num_voxels itself is fetched lazily.
-int voxelmap_attempt(vgicp_handle h, int B) {
-  Cloud& t = h->target;
-  VoxelMap& m = h->map;
+int voxelmap_attempt(vgicp_handle h, Cloud& t, VoxelMap& m, int B) {
   const int n = t.n;
   CU_TRY(h, m.slots.reserve(B));
   KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_fill_i32<<<blocks_for(B, 256), 256, 0, t.st>>>(m.slots.p, -1, (size_t)B));
-  CU_TRY(h, cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(int), t.st));
+  CU_TRY(h, cudaMemsetAsync(m.d_counters, 0, 2 * sizeof(int), t.st));
   KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_table_insert<<<blocks_for(n, 256), 256, 0, t.st>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan));
   KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP,
-             k_table_lookup_points<<<blocks_for(n, 256), 256, 0, t.st>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan, m.slot_of_point.p, h->d_counters));
+             k_table_lookup_points<<<blocks_for(n, 256), 256, 0, t.st>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan, m.slot_of_point.p, m.d_counters));
   CU_TRY(h, cudaGetLastError());
-  CU_TRY(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(int), cudaMemcpyDeviceToHost, t.st));
+  CU_TRY(h, cudaMemcpyAsync(m.h_counters, m.d_counters, sizeof(int), cudaMemcpyDeviceToHost, t.st));
   CU_TRY(h, cudaEventRecord(m.ev_attempt, t.st));
   m.pending_B = B;
   return VGICP_OK;
 }
 
-int voxelmap_begin(vgicp_handle h) {
-  Cloud& t = h->target;
-  VoxelMap& m = h->map;
-  if (!t.has_pts || !t.has_cov) return fail(h, VGICP_ERR_BAD_STATE, "create_target_voxelmap: target points and covariances required");
+int voxelmap_begin(vgicp_handle h, Cloud& t, VoxelMap& m) {
+  if (!t.has_pts || (!m.ndt && !t.has_cov)) return fail(h, VGICP_ERR_BAD_STATE, "create_target_voxelmap: target points and covariances required");
   if (t.n <= 0) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "create_target_voxelmap: empty target cloud");
   if (!m.created) {  // fast_vgicp_cuda.cu:259-261: created once with the resolution current at that time
     m.created = true;
@@ -367,24 +374,22 @@ int voxelmap_begin(vgicp_handle h) {
   CU_TRY(h, m.coords.reserve(n));
   CU_TRY(h, m.slot_of_point.reserve(n));
   KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_coords<<<blocks_for(n, 256), 256, 0, t.st>>>(t.pts.p, n, m.res, m.coords.p));
-  int rc = voxelmap_attempt(h, m.init_num_buckets);
+  int rc = voxelmap_attempt(h, t, m, m.init_num_buckets);
   if (rc) return rc;
   m.pending = true;
   return VGICP_OK;
 }
 
-int voxelmap_finish(vgicp_handle h) {
-  Cloud& t = h->target;
-  VoxelMap& m = h->map;
+int voxelmap_finish(vgicp_handle h, Cloud& t, VoxelMap& m) {
   if (!m.pending) return m.built ? VGICP_OK : fail(h, VGICP_ERR_BAD_STATE, "target voxel map not built");
   const int n = t.n;
   int B = m.pending_B;
   for (;;) {  // :265 (no upper bound in the reference; bounded here)
     CU_TRY(h, cudaEventSynchronize(m.ev_attempt));
-    if ((double)h->h_counters[0] / (double)n < 0.01) break;  // :280
+    if ((double)m.h_counters[0] / (double)n < 0.01) break;  // :280
     B *= 2;
     if (B > (1 << 28)) { m.pending = false; return fail(h, VGICP_ERR_INVALID_ARGUMENT, "create_target_voxelmap: hash table would exceed 2^28 buckets"); }
-    int rc = voxelmap_attempt(h, B);
+    int rc = voxelmap_attempt(h, t, m, B);
     if (rc) return rc;
   }
   m.pending = false;
@@ -394,14 +399,22 @@ int voxelmap_finish(vgicp_handle h) {
   CU_TRY(h, m.vox.reserve(vmax));
   CU_TRY(h, m.sums.reserve((size_t)vmax * 10));
   CU_TRY(h, m.counts.reserve(vmax));
-  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_table_assign_ids<<<1, 1024, 0, t.st>>>(m.coords.p, m.slots.p, B, m.buckets.p, h->d_counters + 1));
+  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_table_assign_ids<<<1, 1024, 0, t.st>>>(m.coords.p, m.slots.p, B, m.buckets.p, m.d_counters + 1));
   CU_TRY(h, cudaMemsetAsync(m.sums.p, 0, sizeof(double) * 10 * (size_t)vmax, t.st));
   CU_TRY(h, cudaMemsetAsync(m.counts.p, 0, sizeof(int) * (size_t)vmax, t.st));
-  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP,
-             k_voxel_accumulate<<<blocks_for(n, 256), 256, 0, t.st>>>(t.pts.p, t.covA.p, t.covB.p, n, m.slot_of_point.p, m.buckets.p, m.sums.p, m.counts.p));
-  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_finalize<<<blocks_for(vmax, 256), 256, 0, t.st>>>(m.sums.p, m.counts.p, h->d_counters + 1, m.vox.p));
+  if (m.ndt) {
+    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_accumulate_ndt<<<blocks_for(n, 256), 256, 0, t.st>>>(t.pts.p, n, m.slot_of_point.p, m.buckets.p, m.sums.p, m.counts.p));
+    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_finalize_ndt<<<blocks_for(vmax, 256), 256, 0, t.st>>>(m.sums.p, m.counts.p, m.d_counters + 1, m.vox.p));
+    cudaError_t ke = cudaSuccess;
+    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, ke = launch_regularize_voxels(m.vox.p, m.d_counters + 1, vmax, VGICP_REG_MIN_EIG, t.st));  // ndt_cuda.cu:129,140
+    CU_TRY(h, ke);
+  } else {
+    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP,
+               k_voxel_accumulate<<<blocks_for(n, 256), 256, 0, t.st>>>(t.pts.p, t.covA.p, t.covB.p, n, m.slot_of_point.p, m.buckets.p, m.sums.p, m.counts.p));
+    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_finalize<<<blocks_for(vmax, 256), 256, 0, t.st>>>(m.sums.p, m.counts.p, m.d_counters + 1, m.vox.p));
+  }
   CU_TRY(h, cudaGetLastError());
-  CU_TRY(h, cudaMemcpyAsync(h->h_counters + 1, h->d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, t.st));
+  CU_TRY(h, cudaMemcpyAsync(m.h_counters + 1, m.d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, t.st));
   CU_TRY(h, cudaEventRecord(m.ev_done, t.st));
   CU_TRY(h, cudaEventRecord(t.ready, t.st));
   m.v_pending = true;
@@ -409,25 +422,26 @@ int voxelmap_finish(vgicp_handle h) {
   return VGICP_OK;
 }
 
-int voxelmap_num_voxels(vgicp_handle h, int* nv) {
-  int rc = voxelmap_finish(h);
+int voxelmap_num_voxels(vgicp_handle h, Cloud& t, VoxelMap& m, int* nv) {
+  int rc = voxelmap_finish(h, t, m);
   if (rc) return rc;
-  VoxelMap& m = h->map;
   if (m.v_pending) {
     CU_TRY(h, cudaEventSynchronize(m.ev_done));
-    m.num_voxels = h->h_counters[1];
+    m.num_voxels = m.h_counters[1];
     m.v_pending = false;
   }
   *nv = m.num_voxels;
   return VGICP_OK;
 }
 
-int build_voxelmap(vgicp_handle h) { return voxelmap_begin(h); }
+int build_voxelmap(vgicp_handle h) { return voxelmap_begin(h, h->target, h->map); }
 
 // everything an evaluation on the main stream depends on: the finished voxel map and the last operations enqueued on the two
 // cloud streams
+int ndt_prepare(vgicp_handle h);
+
 int sync_inputs(vgicp_handle h) {
-  int rc = voxelmap_finish(h);
+  int rc = h->problem == 0 ? voxelmap_finish(h, h->target, h->map) : ndt_prepare(h);
   if (rc) return rc;
   if (h->target.st != h->stream && h->target.ready) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->target.ready, 0));
   if (h->source.st != h->stream && h->source.ready) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->source.ready, 0));
@@ -442,12 +456,18 @@ struct LinLaunch {
 };
 LinLaunch make_lin_launch(vgicp_handle h) {
   Cloud& s = h->source;
-  VoxelMap& m = h->map;
+  VoxelMap& m = h->problem != 0 ? h->ndt_t : h->map;
   LinLaunch L;
   LinArgs& a = L.a;
-  const int sb = h->shard_end >= 0 ? h->shard_begin : 0;
-  const int se = h->shard_end >= 0 ? (h->shard_end < s.n ? h->shard_end : s.n) : s.n;
-  a.pts = s.pts.p + sb; a.covA = s.covA.p + sb; a.covB = s.covB.p + sb; a.n = se > sb ? se - sb : 0;
+  a.ndt = h->problem != 0 ? 1 : 0;
+  if (h->problem != 0) {  // NDT: target map = ndt_t; source = points + zero covariances (P2D) or source voxel Gaussians (D2D)
+    a.pts = h->problem == 2 ? h->ndt_src_pts.p : s.pts.p;
+    a.covA = h->ndt_src_covA.p; a.covB = h->ndt_src_covB.p; a.n = h->ndt_src_n;
+  } else {
+    const int sb = h->shard_end >= 0 ? h->shard_begin : 0;
+    const int se = h->shard_end >= 0 ? (h->shard_end < s.n ? h->shard_end : s.n) : s.n;
+    a.pts = s.pts.p + sb; a.covA = s.covA.p + sb; a.covB = s.covB.p + sb; a.n = se > sb ? se - sb : 0;
+  }
   a.comm_ranks = h->comm_ranks; a.comm_rank = h->comm_rank; a.comm_seq = 0;
   for (int r = 0; r < kCommMaxRanks; r++) a.comm_peers[r] = h->comm_peers[r];
   a.buckets = m.buckets.p; a.mask = (unsigned)(m.num_buckets - 1); a.max_scan = m.max_scan; a.vox = m.vox.p;
@@ -538,9 +558,53 @@ int launch_lm_step(vgicp_handle h, const LinLaunch& L) {
 }
 
 int check_ready_for_eval(vgicp_handle h, const char* who) {
+  if (h->problem != 0) {
+    if (!h->source.has_pts || !h->target.has_pts) return fail(h, VGICP_ERR_BAD_STATE, std::string(who) + ": NDT needs source and target clouds");
+    if (!h->has_lin) return fail(h, VGICP_ERR_BAD_STATE, std::string(who) + ": update_correspondences has not been called");
+    return VGICP_OK;
+  }
   if (!h->source.has_pts || !h->source.has_cov) return fail(h, VGICP_ERR_BAD_STATE, std::string(who) + ": source points and covariances required");
   if (!h->map.built && !h->map.pending) return fail(h, VGICP_ERR_BAD_STATE, std::string(who) + ": target voxel map not built");
   if (!h->has_lin) return fail(h, VGICP_ERR_BAD_STATE, std::string(who) + ": update_correspondences has not been called");
+  return VGICP_OK;
+}
+
+// builds what an NDT evaluation needs (idempotent): target map, and for D2D the source map + its Gaussians as a cloud
+int ndt_prepare(vgicp_handle h) {
+  if (h->ndt_ready) return VGICP_OK;
+  Cloud& t = h->target;
+  Cloud& s = h->source;
+  if (!t.has_pts || !s.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "NDT: source and target clouds required");
+  if (t.n <= 0 || s.n <= 0) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "NDT: empty cloud");
+  for (VoxelMap* vm : {&h->ndt_t, &h->ndt_s}) {
+    vm->created = true;
+    vm->res = (float)h->resolution;  // NDT maps are re-created with the current resolution (ndt_cuda.cu:127,138)
+  }
+  int rc;
+  if ((rc = voxelmap_begin(h, t, h->ndt_t))) return rc;
+  if (h->problem == 2 && (rc = voxelmap_begin(h, s, h->ndt_s))) return rc;
+  if ((rc = voxelmap_finish(h, t, h->ndt_t))) return rc;
+  if (h->problem == 2) {
+    int vs = 0;
+    if ((rc = voxelmap_num_voxels(h, s, h->ndt_s, &vs))) return rc;
+    CU_TRY(h, h->ndt_src_pts.reserve(vs > 0 ? vs : 1));
+    CU_TRY(h, h->ndt_src_covA.reserve(vs > 0 ? vs : 1));
+    CU_TRY(h, h->ndt_src_covB.reserve(vs > 0 ? vs : 1));
+    if (vs > 0)
+      KLAUNCH_ST(h, s.st, VGICP_PROF_VOXELMAP,
+                 k_vox_to_cloud<<<blocks_for(vs, 256), 256, 0, s.st>>>(h->ndt_s.vox.p, h->ndt_s.d_counters + 1, h->ndt_src_pts.p, h->ndt_src_covA.p, h->ndt_src_covB.p));
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaEventRecord(s.ready, s.st));
+    h->ndt_src_n = vs;
+  } else {
+    CU_TRY(h, h->ndt_src_covA.reserve(s.n));
+    CU_TRY(h, h->ndt_src_covB.reserve(s.n));
+    CU_TRY(h, cudaMemsetAsync(h->ndt_src_covA.p, 0, sizeof(float4) * (size_t)s.n, s.st));
+    CU_TRY(h, cudaMemsetAsync(h->ndt_src_covB.p, 0, sizeof(float2) * (size_t)s.n, s.st));
+    CU_TRY(h, cudaEventRecord(s.ready, s.st));
+    h->ndt_src_n = s.n;
+  }
+  h->ndt_ready = true;
   return VGICP_OK;
 }
 
@@ -603,17 +667,20 @@ int vgicp_create(int device, vgicp_handle* out) {
   ok = ok && cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&h->target.ready, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&h->source.ready, cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && cudaEventCreateWithFlags(&h->map.ev_attempt, cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && cudaEventCreateWithFlags(&h->map.ev_done, cudaEventDisableTiming) == cudaSuccess;
   h->target.st = h->stream;    // the target (and its voxel map) is built on the main stream, where the evaluations run
   h->source.st = h->stream_b;  // the source's stage 1 overlaps with it
   ok = ok && cudaMalloc(&h->d_ticket, sizeof(unsigned int)) == cudaSuccess;
-  ok = ok && cudaMalloc(&h->d_counters, 4 * sizeof(int)) == cudaSuccess;
+  for (VoxelMap* vm : {&h->map, &h->ndt_t, &h->ndt_s}) {
+    ok = ok && cudaMalloc(&vm->d_counters, 4 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&vm->h_counters, 4 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&vm->ev_attempt, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&vm->ev_done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  h->ndt_t.ndt = h->ndt_s.ndt = 1;
   ok = ok && cudaMalloc(&h->d_out, 64 * sizeof(double)) == cudaSuccess;
   ok = ok && cudaHostAlloc(&h->h_out, 64 * sizeof(double), cudaHostAllocMapped) == cudaSuccess;
   ok = ok && cudaHostAlloc(&h->h_flag, 64, cudaHostAllocMapped) == cudaSuccess;
   if (ok) *h->h_flag = 0;
-  ok = ok && cudaMallocHost(&h->h_counters, 4 * sizeof(int)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->d_lm, sizeof(LmState)) == cudaSuccess;
   ok = ok && cudaMallocHost(&h->h_lm, sizeof(LmState)) == cudaSuccess;
   ok = ok && h->partials.reserve((size_t)kLinMaxBlocks * kLinValues) == cudaSuccess;
@@ -636,7 +703,6 @@ int vgicp_destroy(vgicp_handle h) {
   if (h->stream_b) cudaStreamSynchronize(h->stream_b);
   h->source.release();
   h->target.release();
-  h->map.release();
   h->d_offsets.release();
   h->staging.release();
   if (h->comm_ranks > 1) vgicp_comm_shutdown(h);
@@ -644,16 +710,22 @@ int vgicp_destroy(vgicp_handle h) {
   h->partials.release();
   h->corr_ids.release();
   if (h->d_ticket) cudaFree(h->d_ticket);
-  if (h->d_counters) cudaFree(h->d_counters);
+  for (VoxelMap* vm : {&h->map, &h->ndt_t, &h->ndt_s}) {
+    if (vm->d_counters) cudaFree(vm->d_counters);
+    if (vm->h_counters) cudaFreeHost(vm->h_counters);
+    if (vm->ev_attempt) cudaEventDestroy(vm->ev_attempt);
+    if (vm->ev_done) cudaEventDestroy(vm->ev_done);
+    vm->release();
+  }
+  h->ndt_src_pts.release(); h->ndt_src_covA.release(); h->ndt_src_covB.release();
   if (h->d_out) cudaFree(h->d_out);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_flag) cudaFreeHost(h->h_flag);
-  if (h->h_counters) cudaFreeHost(h->h_counters);
   if (h->d_lm) cudaFree(h->d_lm);
   if (h->h_lm) cudaFreeHost(h->h_lm);
   for (auto& r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : h->prof_pool) cudaEventDestroy(e);
-  for (cudaEvent_t e : {h->ev_copy, h->target.ready, h->source.ready, h->map.ev_attempt, h->map.ev_done})
+  for (cudaEvent_t e : {h->ev_copy, h->target.ready, h->source.ready})
     if (e) cudaEventDestroy(e);
   if (h->stream_b) cudaStreamDestroy(h->stream_b);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -744,12 +816,14 @@ int vgicp_swap_source_and_target(vgicp_handle h) {  // fast_vgicp_cuda.cu:97-107
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
   // the clouds keep their streams; everything in flight (incl. a pending map build that reads the old target) must land first
-  if (h->map.pending) { int rc0 = voxelmap_finish(h); if (rc0) return rc0; }
+  if (h->map.pending) { int rc0 = voxelmap_finish(h, h->target, h->map); if (rc0) return rc0; }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream_b));
   std::swap(h->source, h->target);
   h->map.built = false;
   h->map.pending = false;
+  h->ndt_ready = false;  // NDT: the reference swaps its two maps (ndt_cuda.cu:93-96); here they are rebuilt on demand
+  if (h->problem != 0) return VGICP_OK;
   if (!h->target.has_pts || !h->target.has_cov) return VGICP_OK;
   return build_voxelmap(h);
 }
@@ -837,24 +911,29 @@ int vgicp_get_num_voxels(vgicp_handle h, int* nv) {
   CHECK_HANDLE(h);
   if (!nv) return VGICP_ERR_INVALID_ARGUMENT;
   DeviceGuard g(h->device);
-  return voxelmap_num_voxels(h, nv);
+  if (h->problem != 0) { int rc = ndt_prepare(h); if (rc) return rc; return voxelmap_num_voxels(h, h->target, h->ndt_t, nv); }
+  return voxelmap_num_voxels(h, h->target, h->map, nv);
 }
 int vgicp_get_num_buckets(vgicp_handle h, int* nb) {
   CHECK_HANDLE(h);
   if (!nb) return VGICP_ERR_INVALID_ARGUMENT;
   DeviceGuard g(h->device);
-  { int rc = voxelmap_finish(h); if (rc) return rc; }
+  if (h->problem != 0) { int rc = ndt_prepare(h); if (rc) return rc; *nb = h->ndt_t.num_buckets; return VGICP_OK; }
+  { int rc = voxelmap_finish(h, h->target, h->map); if (rc) return rc; }
   *nb = h->map.num_buckets;
   return VGICP_OK;
 }
 
 static int fetch_voxels(vgicp_handle h, std::vector<VoxelRec>& v) {
   int nv = 0;
-  int rc = voxelmap_num_voxels(h, &nv);
+  VoxelMap& vm = h->problem != 0 ? h->ndt_t : h->map;
+  int rc = h->problem != 0 ? ndt_prepare(h) : VGICP_OK;
+  if (rc) return rc;
+  rc = voxelmap_num_voxels(h, h->target, vm, &nv);
   if (rc) return rc;
   v.resize(nv);
   if (!v.empty()) {
-    CU_TRY(h, cudaMemcpyAsync(v.data(), h->map.vox.p, sizeof(VoxelRec) * v.size(), cudaMemcpyDeviceToHost, h->target.st));
+    CU_TRY(h, cudaMemcpyAsync(v.data(), vm.vox.p, sizeof(VoxelRec) * v.size(), cudaMemcpyDeviceToHost, h->target.st));
     CU_TRY(h, cudaStreamSynchronize(h->target.st));
   }
   return VGICP_OK;
@@ -899,11 +978,12 @@ int vgicp_get_voxel_covs(vgicp_handle h, float* out9, size_t cap) {
 int vgicp_get_voxel_buckets(vgicp_handle h, int* coords3, int* ids, size_t cap) {
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
-  { int rc = voxelmap_finish(h); if (rc) return rc; }
-  size_t B = (size_t)h->map.num_buckets;
+  VoxelMap& vm = h->problem != 0 ? h->ndt_t : h->map;
+  { int rc = h->problem != 0 ? ndt_prepare(h) : voxelmap_finish(h, h->target, h->map); if (rc) return rc; }
+  size_t B = (size_t)vm.num_buckets;
   if (cap < B || !coords3 || !ids) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "get_voxel_buckets: buffer too small");
   std::vector<int4> b(B);
-  CU_TRY(h, cudaMemcpyAsync(b.data(), h->map.buckets.p, sizeof(int4) * B, cudaMemcpyDeviceToHost, h->target.st));
+  CU_TRY(h, cudaMemcpyAsync(b.data(), vm.buckets.p, sizeof(int4) * B, cudaMemcpyDeviceToHost, h->target.st));
   CU_TRY(h, cudaStreamSynchronize(h->target.st));
   for (size_t i = 0; i < B; i++) {
     coords3[3 * i] = b[i].x; coords3[3 * i + 1] = b[i].y; coords3[3 * i + 2] = b[i].z;
@@ -916,7 +996,8 @@ int vgicp_update_correspondences(vgicp_handle h, const double T[16]) {  // fast_
   CHECK_HANDLE(h);
   if (!T) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "update_correspondences: null pose");
   if (!h->source.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "update_correspondences: source cloud not set");
-  if (!h->map.built && !h->map.pending) return fail(h, VGICP_ERR_BAD_STATE, "update_correspondences: target voxel map not built");
+  if (h->problem == 0 && !h->map.built && !h->map.pending) return fail(h, VGICP_ERR_BAD_STATE, "update_correspondences: target voxel map not built");
+  if (h->problem != 0 && !h->target.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "update_correspondences: target cloud not set");
   h->lin = to_pose(T);  // linearized_x = trans.cast<float>()
   h->has_lin = true;
   // the lookup itself is fused into the evaluation kernel; the explicit list is only built by the getter
@@ -926,18 +1007,18 @@ int vgicp_update_correspondences(vgicp_handle h, const double T[16]) {  // fast_
 int vgicp_get_voxel_correspondences(vgicp_handle h, int* pairs, size_t cap, size_t* n_pairs) {
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
-  if (!h->source.has_pts || (!h->map.built && !h->map.pending) || !h->has_lin)
+  if (!h->source.has_pts || (h->problem == 0 && !h->map.built && !h->map.pending) || !h->has_lin)
     return fail(h, VGICP_ERR_BAD_STATE, "get_voxel_correspondences: update_correspondences has not been called");
   { int rc = sync_inputs(h); if (rc) return rc; }
-  const int n = h->source.n;
+  const LinLaunch LL = make_lin_launch(h);  // same source array / map as an evaluation (VGICP points, NDT points or voxel means)
+  const int n = LL.a.n;
   const int n_off = (int)h->h_offsets.size();
   size_t total = (size_t)n * n_off;
   std::vector<int> ids(total);
   if (total) {
     CU_TRY(h, h->corr_ids.reserve(total));
     KLAUNCH(h, VGICP_PROF_OTHER,
-            k_correspondence_ids<<<blocks_for(n, 128), 128, 0, h->stream>>>(h->source.pts.p, n, h->map.buckets.p, (unsigned)(h->map.num_buckets - 1), h->map.max_scan, h->d_offsets.p,
-                                                                             n_off, h->map.res, h->lin, h->corr_ids.p));
+            k_correspondence_ids<<<blocks_for(n, 128), 128, 0, h->stream>>>(LL.a.pts, n, LL.a.buckets, LL.a.mask, LL.a.max_scan, h->d_offsets.p, n_off, LL.a.res, h->lin, h->corr_ids.p));
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaMemcpyAsync(ids.data(), h->corr_ids.p, total * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -983,8 +1064,12 @@ int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* 
   if (!guess || !res) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "align: null argument");
   vgicp_lsq_params P;
   if (params) P = *params; else vgicp_lsq_default_params(&P);
-  if (!h->source.has_pts || !h->source.has_cov) return fail(h, VGICP_ERR_BAD_STATE, "align: source points and covariances required");
-  if (!h->map.built && !h->map.pending) return fail(h, VGICP_ERR_BAD_STATE, "align: target voxel map not built");
+  if (h->problem == 0) {
+    if (!h->source.has_pts || !h->source.has_cov) return fail(h, VGICP_ERR_BAD_STATE, "align: source points and covariances required");
+    if (!h->map.built && !h->map.pending) return fail(h, VGICP_ERR_BAD_STATE, "align: target voxel map not built");
+  } else if (!h->source.has_pts || !h->target.has_pts) {
+    return fail(h, VGICP_ERR_BAD_STATE, "align: NDT needs source and target clouds");
+  }
   { int rc = sync_inputs(h); if (rc) return rc; }
 
   if (h->align_mode == 0 && h->comm_ranks <= 1) {
@@ -1227,6 +1312,23 @@ int vgicp_clear_source_shard(vgicp_handle h) {
   return VGICP_OK;
 }
 
+// ---- NDT (NDTCudaCore, src/fast_gicp/cuda/ndt_cuda.cu) on the same handle -------------------------------------------------
+int vgicp_set_problem(vgicp_handle h, int problem) {
+  CHECK_HANDLE(h);
+  if (problem < 0 || problem > 2) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_problem: 0 VGICP, 1 NDT P2D, 2 NDT D2D");
+  if (problem != h->problem) { h->ndt_ready = false; h->has_lin = false; }
+  h->problem = problem;
+  return VGICP_OK;
+}
+
+int vgicp_ndt_create_voxelmaps(vgicp_handle h) {  // NDTCudaCore::create_voxelmaps, ndt_cuda.cu:118-141
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (h->problem == 0) return fail(h, VGICP_ERR_BAD_STATE, "ndt_create_voxelmaps: select an NDT problem first (vgicp_set_problem)");
+  h->ndt_ready = false;
+  return ndt_prepare(h);
+}
+
 int vgicp_set_execution_hint(vgicp_handle h, int hint) {
   CHECK_HANDLE(h);
   if (hint < 0 || hint > 1) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_execution_hint: 0 latency, 1 throughput");
@@ -1319,7 +1421,7 @@ int vgicp_get_launch_count(vgicp_handle h, uint64_t* launches) {
 int vgicp_synchronize(vgicp_handle h) {
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
-  if (h->map.pending) { int rc = voxelmap_finish(h); if (rc) return rc; }
+  if (h->map.pending) { int rc = voxelmap_finish(h, h->target, h->map); if (rc) return rc; }
   CU_TRY(h, cudaStreamSynchronize(h->stream_b));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   return VGICP_OK;

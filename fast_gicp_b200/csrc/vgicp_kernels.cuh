@@ -42,11 +42,6 @@ struct CommMailbox {
   volatile int error;                                // set when a wait times out
 };
 
-struct VoxelRec {
-  float4 mean_n;  // mean xyz, num_points as int bits in w
-  float4 c0;      // cxx cxy cxz cyy
-  float4 c1;      // cyz czz 0 0
-};
 
 // ---------------------------------------------------------------------------------------------------------------
 // vector3_hash.cuh:8-38
@@ -251,6 +246,48 @@ __global__ void k_voxel_finalize(const double* __restrict__ sums, const int* __r
   vox[v] = r;
 }
 
+// NDT voxel maps are built from the points alone (gaussian_voxelmap.cu:122-148): sums of p and p p^T (double, order-free)
+__global__ void k_voxel_accumulate_ndt(const float4* __restrict__ pts, int n, const int* __restrict__ slot_of_point, const int4* __restrict__ buckets, double* __restrict__ sums,
+                                       int* __restrict__ counts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int s = slot_of_point[i];
+  if (s < 0) return;
+  int id = buckets[s].w;
+  float4 p = pts[i];
+  double x = (double)p.x, y = (double)p.y, z = (double)p.z;
+  double* d = sums + (size_t)id * 10;
+  atomicAdd(&counts[id], 1);
+  atomicAdd(d + 0, x); atomicAdd(d + 1, y); atomicAdd(d + 2, z);
+  atomicAdd(d + 3, x * x); atomicAdd(d + 4, x * y); atomicAdd(d + 5, x * z);
+  atomicAdd(d + 6, y * y); atomicAdd(d + 7, y * z); atomicAdd(d + 8, z * z);
+}
+
+// ndt_finalize_voxels_kernel (gaussian_voxelmap.cu:178-198): mean = sum/n ; cov = (sum_ppT - mean * sum^T) / n
+__global__ void k_voxel_finalize_ndt(const double* __restrict__ sums, const int* __restrict__ counts, const int* __restrict__ nv_ptr, VoxelRec* __restrict__ vox) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= *nv_ptr) return;
+  int c = counts[v];
+  double nn = (double)c;
+  const double* d = sums + (size_t)v * 10;
+  double mx = d[0] / nn, my = d[1] / nn, mz = d[2] / nn;
+  VoxelRec r;
+  r.mean_n = make_float4((float)mx, (float)my, (float)mz, __int_as_float(c));
+  r.c0 = make_float4((float)((d[3] - mx * d[0]) / nn), (float)((d[4] - my * d[0]) / nn), (float)((d[5] - mz * d[0]) / nn), (float)((d[6] - my * d[1]) / nn));
+  r.c1 = make_float4((float)((d[7] - mz * d[1]) / nn), (float)((d[8] - mz * d[2]) / nn), 0.f, 0.f);
+  vox[v] = r;
+}
+
+// D2D: the source voxel means / covariances become the "source cloud" of the evaluation kernel
+__global__ void k_vox_to_cloud(const VoxelRec* __restrict__ vox, const int* __restrict__ nv_ptr, float4* __restrict__ pts, float4* __restrict__ covA, float2* __restrict__ covB) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= *nv_ptr) return;
+  VoxelRec r = vox[v];
+  pts[v] = make_float4(r.mean_n.x, r.mean_n.y, r.mean_n.z, 0.f);
+  covA[v] = r.c0;
+  covB[v] = make_float2(r.c1.x, r.c1.y);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Stage 2b + 3 fused: per source point, transform by the linearisation pose, probe the neighbour voxels
 // (find_voxel_correspondences.cu:32-60), and accumulate the Mahalanobis residual and Jacobian terms
@@ -271,6 +308,7 @@ struct LinArgs {
   const int4* offsets;  // generic mode
   int n_off;
   float res;
+  int ndt;  // 0: VGICP weights (sqrt(n), compute_derivatives.cu:78); 1: NDT (Cauchy weight, voxels with <= 6 points skipped, ndt_compute_derivatives.cu)
   Pose Tlin, Teval;
   double* partials;       // [gridDim.x][kLinValues]
   unsigned int* ticket;   // zero before first launch; reset by the last block
@@ -307,17 +345,25 @@ struct PointAcc {
 // `hit` = false contributes exactly zero (the voxel record read for a miss is voxel 0, only there to keep the load
 // unconditional so that all loads of a lane can be in flight together).
 template <bool WANT_H>
-__device__ __forceinline__ void accumulate_voxel(float4 mn, float4 c0, float4 c1, bool hit, const float* rcr, float3 pe, PointAcc<WANT_H>& acc) {
+__device__ __forceinline__ void accumulate_voxel(float4 mn, float4 c0, float4 c1, bool hit, const float* rcr, float3 pe, PointAcc<WANT_H>& acc, int ndt, float res) {
   int np = __float_as_int(mn.w);
-  if (WANT_H && np <= 0) hit = false;  // compute_derivatives.cu:62-64
+  if (ndt ? (np <= 6) : (WANT_H && np <= 0)) hit = false;  // ndt_compute_derivatives.cu:61,132 / compute_derivatives.cu:62-64
   float a = c0.x + rcr[0], b = c0.y + rcr[1], c = c0.z + rcr[2], d = c0.w + rcr[3], e = c1.x + rcr[4], f = c1.y + rcr[5];
   float k00 = d * f - e * e, k01 = c * e - b * f, k02 = b * e - c * d;
   float det = (a * k00 + b * k01) + c * k02;
   float id_ = 1.0f / det;
   float m00 = k00 * id_, m01 = k01 * id_, m02 = k02 * id_;
   float m11 = (a * f - c * c) * id_, m12 = (b * c - a * e) * id_, m22 = (a * d - b * b) * id_;
-  float w = hit ? sqrtf((float)np) : 0.0f;
   float ex = mn.x - pe.x, ey = mn.y - pe.y, ez = mn.z - pe.z;
+  float w;
+  if (ndt) {  // cauchy(resolution, |e|) = k^2 / (k^2 + x^2), ndt_compute_derivatives.cu:15-18,78,150
+    float x = sqrtf((ex * ex + ey * ey) + ez * ez);
+    float k_sq = res * res;
+    w = k_sq / (k_sq + x * x);
+  } else {
+    w = sqrtf((float)np);
+  }
+  if (!hit) w = 0.0f;
   float mex = (m00 * ex + m01 * ey) + m02 * ez;
   float mey = (m01 * ex + m11 * ey) + m12 * ez;
   float mez = (m02 * ex + m12 * ey) + m22 * ez;
@@ -441,7 +487,7 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl,
         mn[j] = __ldg(vr); c0[j] = __ldg(vr + 1); c1[j] = __ldg(vr + 2);
       }
 #pragma unroll
-      for (int j = 0; j < CELLS; j++) accumulate_voxel<WANT_H>(mn[j], c0[j], c1[j], id[j] >= 0, rcr, pe, acc);
+      for (int j = 0; j < CELLS; j++) accumulate_voxel<WANT_H>(mn[j], c0[j], c1[j], id[j] >= 0, rcr, pe, acc, a.ndt, a.res);
     }
 
     if (WANT_H) {

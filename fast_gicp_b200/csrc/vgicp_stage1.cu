@@ -838,9 +838,27 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid_heavy(GridArgs 
   }
 }
 
+// regulariser over voxel covariances (NDT).  The finalised covariance (S_rc - mean_r * S_c)/n is symmetric only up to rounding;
+// Eigen's selfadjointView<Lower> reads the lower triangle, which is what the packed record holds.
+__global__ void k_regularize_voxels(VoxelRec* __restrict__ vox, const int* __restrict__ nv_ptr, int method) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= *nv_ptr) return;
+  VoxelRec r = vox[v];
+  float c[9] = {r.c0.x, r.c0.y, r.c0.z, r.c0.y, r.c0.w, r.c1.x, r.c0.z, r.c1.x, r.c1.y};
+  regularize_cov(c, method);
+  r.c0 = make_float4(c[0], 0.5f * (c[1] + c[3]), 0.5f * (c[2] + c[6]), c[4]);
+  r.c1 = make_float4(0.5f * (c[5] + c[7]), c[8], 0.f, 0.f);
+  vox[v] = r;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------------
+cudaError_t launch_regularize_voxels(VoxelRec* vox, const int* nv_ptr, int vmax, int method, cudaStream_t stream) {
+  k_regularize_voxels<<<(vmax + 127) / 128, 128, 0, stream>>>(vox, nv_ptr, method);
+  return cudaGetLastError();
+}
+
 size_t knn_smem_bytes(int k) { return sizeof(float4) * kKnnTile + (size_t)k * kKnnThreads * (sizeof(float) + sizeof(int)); }
 
 cudaError_t launch_knn_bruteforce(const float4* pts, int n, int k, int* nbr, cudaStream_t stream) {

@@ -5,6 +5,12 @@
 
 namespace vgicp {
 
+struct VoxelRec {
+  float4 mean_n;  // mean xyz, num_points as int bits in w
+  float4 c0;      // cxx cxy cxz cyy
+  float4 c1;      // cyz czz 0 0
+};
+
 constexpr int kMaxK = 64;         // k-NN list capacity
 constexpr int kKnnThreads = 128;  // queries per block in the brute-force k-NN
 constexpr int kKnnTile = 512;     // targets staged in shared memory per step
@@ -20,5 +26,9 @@ cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned 
 cudaError_t launch_covariance_knn(const float4* pts, const int* nbr, int n, int k, int method, float4* covA, float2* covB, cudaStream_t stream);
 // covariance_estimation_rbf + covariance_regularization(method)
 cudaError_t launch_covariance_rbf(const float4* pts, int n, float exp_factor, float max_dist, int method, float4* covA, float2* covB, cudaStream_t stream);
+
+// covariance_regularization(method) over the covariances of a voxel array (NDT: MIN_EIG on voxel covariances, ndt_cuda.cu:129,140);
+// launched for `vmax` voxels, the exact count is read from *nv_ptr on the device
+cudaError_t launch_regularize_voxels(VoxelRec* vox, const int* nv_ptr, int vmax, int method, cudaStream_t stream);
 
 }  // namespace vgicp

@@ -126,6 +126,91 @@ class LsqRegistration:
         return self.getFitnessScore(max_range)
 
 
+class NDTDistanceMode(enum.IntEnum):  # ndt_settings.hpp:6
+    P2D = 0
+    D2D = 1
+
+
+class NDTCuda(LsqRegistration):
+    """fast_gicp::NDTCuda (include/fast_gicp/ndt/ndt_cuda.hpp:22-71, impl/ndt_cuda_impl.hpp:11-90) on the same engine:
+    voxel Gaussians from the raw points (MIN_EIG-regularised), Cauchy-weighted P2D / D2D residuals, DIRECT7 by default."""
+
+    def __init__(self, device=0):
+        super().__init__()
+        self.reg_name_ = "NDTCuda"
+        self.ndt_cuda_ = Core(device)
+        self._mode = NDTDistanceMode.D2D  # ndt_cuda.cu:21
+        self.ndt_cuda_.set_problem(2)
+        self.ndt_cuda_.set_neighbor_search_method(int(NeighborSearchMethod.DIRECT7), 0.0)  # ndt_cuda.cu:22
+
+    def setDistanceMode(self, mode):
+        self._mode = NDTDistanceMode(mode)
+        self.ndt_cuda_.set_problem(1 if self._mode == NDTDistanceMode.P2D else 2)
+
+    def setResolution(self, resolution):
+        self.ndt_cuda_.set_resolution(resolution)
+
+    def setNeighborSearchMethod(self, method, radius=-1.0):
+        if isinstance(method, str):
+            method = NeighborSearchMethod[method]
+        self.ndt_cuda_.set_neighbor_search_method(int(method), radius)
+
+    # pygicp names (main.cpp:204-212)
+    def set_resolution(self, r):
+        self.setResolution(r)
+
+    def set_neighbor_search_method(self, method="DIRECT1", radius=1.5):
+        self.setNeighborSearchMethod(method, radius)
+
+    def swapSourceAndTarget(self):
+        self.ndt_cuda_.swap_source_and_target()
+        self.input_, self.target_ = self.target_, self.input_
+
+    def clearSource(self):
+        self.input_ = None
+
+    def clearTarget(self):
+        self.target_ = None
+
+    def setInputSource(self, cloud):
+        if cloud is self.input_:
+            return
+        self.input_ = cloud
+        self.ndt_cuda_.set_source_cloud(cloud)
+
+    def setInputTarget(self, cloud):
+        if cloud is self.target_:
+            return
+        self.target_ = cloud
+        self.ndt_cuda_.set_target_cloud(cloud)
+
+    def linearize(self, trans):
+        return self.ndt_cuda_.linearize(trans)
+
+    def compute_error(self, trans):
+        return self.ndt_cuda_.compute_error(trans, want_H=False)[0]
+
+    def align(self, initial_guess=None, aligned_out=None):
+        if self.input_ is None or self.target_ is None:
+            raise RuntimeError("align: input source/target not set")
+        guess = np.eye(4) if initial_guess is None else np.asarray(initial_guess, dtype=np.float32).astype(np.float64)
+        self.ndt_cuda_.ndt_create_voxelmaps()  # computeTransformation, ndt_cuda_impl.hpp:71-73
+        self.converged_ = False
+        res = self.ndt_cuda_.align(guess, self._params())
+        if res.lm_failed:
+            print("lm not converged!!")
+        self.nr_iterations_ = res.nr_iterations
+        self.converged_ = bool(res.converged)
+        self.final_hessian_ = np.array(res.H).reshape(6, 6).T.copy()
+        self.final_transformation_ = _core.pose_from_c(res.T).astype(np.float32)
+        if aligned_out is not None:
+            self.ndt_cuda_.transform_source(self.final_transformation_.astype(np.float64), out=aligned_out)
+        return self.final_transformation_
+
+    def getFitnessScore(self, max_range=float("inf")):
+        return self.ndt_cuda_.fitness_score(self.final_transformation_.astype(np.float64), max_range)
+
+
 class FastVGICPCuda(LsqRegistration):
     """Fast Voxelized GICP on a B200 behind the reference's FastVGICPCuda interface."""
 

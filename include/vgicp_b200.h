@@ -168,6 +168,17 @@ VGICP_API int vgicp_comm_shutdown(vgicp_handle h);
 VGICP_API int vgicp_comm_error(vgicp_handle h, int* error);  /* 1 when a wait for a peer timed out */
 VGICP_API int vgicp_set_source_shard(vgicp_handle h, size_t begin, size_t end);  /* evaluations cover source points [begin, end) */
 VGICP_API int vgicp_clear_source_shard(vgicp_handle h);
+/* ---- NDT (next-tier component: fast_gicp::cuda::NDTCudaCore, include/fast_gicp/cuda/ndt_cuda.cuh:28-68, src/fast_gicp/cuda/ndt_cuda.cu) ----
+ * The same handle solves the NDT problems: vgicp_set_problem selects VGICP (0, default), NDT point-to-distribution (1) or NDT
+ * distribution-to-distribution (2; NDTDistanceMode order P2D, D2D of ndt_settings.hpp:6, plus one).  With an NDT problem selected
+ *   set_{source,target}_cloud, set_resolution, set_neighbor_search_method, swap_source_and_target   as NDTCudaCore's members (:36-48)
+ *   vgicp_ndt_create_voxelmaps      NDTCudaCore::create_voxelmaps (ndt_cuda.cu:118-141): points-only voxel Gaussians + MIN_EIG
+ *   vgicp_update_correspondences    NDTCudaCore::update_correspondences (:143-162): source points (P2D) or source voxel means (D2D)
+ *   vgicp_compute_error / vgicp_align   NDTCudaCore::compute_error (:164-177) -> {p2d,d2d}_ndt_compute_derivatives
+ *   vgicp_get_voxel_* / vgicp_get_num_voxels / vgicp_get_voxel_buckets   read the NDT target map
+ * No kNN and no per-point covariances are involved (the reference's NDTCuda never computes them). */
+VGICP_API int vgicp_set_problem(vgicp_handle h, int problem);
+VGICP_API int vgicp_ndt_create_voxelmaps(vgicp_handle h);
 /* Launch-shape hint: 0 = latency (default; one registration should finish as soon as possible: a point's neighbour cells are
  * split over several lanes, the persistent k-NN kernel takes 4 blocks per SM), 1 = throughput (many handles share the GPU on
  * separate streams: one lane per point and 2 k-NN blocks per SM -- fewer instructions per registration, longer kernels).

@@ -70,6 +70,11 @@ def lib():
         L.orc_regularize.argtypes = [fp, C.c_int, C.c_int]
         L.orc_voxelmap_build.restype = vp
         L.orc_voxelmap_build.argtypes = [fp, fp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_ndt_voxelmap_build.restype = vp
+        L.orc_ndt_voxelmap_build.argtypes = [fp, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_align_ndt.argtypes = [vp, fp, fp, C.c_int, ip, C.c_int, C.POINTER(LsqParams), dp, C.c_int, C.POINTER(LsqResult)]
+        L.orc_evaluate_ndt.restype = C.c_double
+        L.orc_evaluate_ndt.argtypes = [vp, fp, fp, C.c_int, ip, C.c_int, dp, dp, dp, dp, C.c_int, C.POINTER(C.c_long)]
         L.orc_voxelmap_free.argtypes = [vp]
         L.orc_voxelmap_num_buckets.argtypes = [vp]
         L.orc_voxelmap_num_voxels.argtypes = [vp]
@@ -198,9 +203,15 @@ class VoxelMap:
     """GaussianVoxelMap (gaussian_voxelmap.cu) built by the oracle."""
 
     def __init__(self, pts, cov9, res=1.0, init_buckets=8192, max_scan=10, accum_double=False):
-        self.pts, self.cov = _f32(pts), _f32(cov9)
+        """cov9=None builds the NDT map (points only, MIN_EIG-regularised voxel covariances)."""
+        self.pts = _f32(pts)
         L = lib()
-        self._h = L.orc_voxelmap_build(_p(self.pts, C.c_float), _p(self.cov, C.c_float), len(self.pts), C.c_float(res), init_buckets, max_scan, int(accum_double))
+        if cov9 is None:
+            self.cov = None
+            self._h = L.orc_ndt_voxelmap_build(_p(self.pts, C.c_float), len(self.pts), C.c_float(res), init_buckets, max_scan, int(accum_double))
+        else:
+            self.cov = _f32(cov9)
+            self._h = L.orc_voxelmap_build(_p(self.pts, C.c_float), _p(self.cov, C.c_float), len(self.pts), C.c_float(res), init_buckets, max_scan, int(accum_double))
         self.res = float(np.float32(res))
         self.num_buckets = L.orc_voxelmap_num_buckets(self._h)
         self.num_voxels = L.orc_voxelmap_num_voxels(self._h)
@@ -273,6 +284,40 @@ def align_f32(vmap, src, src_cov, offs, guess=None, params=None, sum_float=False
     g = _pose_in(np.eye(4) if guess is None else guess)
     r = LsqResult()
     lib().orc_align_f32(vmap._h, _p(src, C.c_float), _p(src_cov, C.c_float), len(src), _p(offs, C.c_int), len(offs), C.byref(params), _p(g, C.c_double), int(sum_float), C.byref(r))
+    return AlignResult(r)
+
+
+P2D, D2D = 0, 1  # ndt_settings.hpp:6
+
+
+def _ndt_source(source, res, mode, accum_double):
+    if mode == P2D:
+        return _f32(source), None, None
+    sm = VoxelMap(source, None, res, accum_double=accum_double)
+    return sm.vox_mean.copy(), sm.vox_cov.copy(), sm
+
+
+def evaluate_ndt(vmap, src, src_cov, offs, T_lin, T_eval, want_H=True, sum_float=False):
+    src, offs = _f32(src), _i32(offs)
+    cov_p = _p(_f32(src_cov), C.c_float) if src_cov is not None else None
+    H = np.zeros(36)
+    b = np.zeros(6)
+    nc = C.c_long(0)
+    e = lib().orc_evaluate_ndt(vmap._h, _p(src, C.c_float), cov_p, len(src), _p(offs, C.c_int), len(offs), _p(_pose_in(T_lin), C.c_double), _p(_pose_in(T_eval), C.c_double),
+                               _p(H, C.c_double) if want_H else None, _p(b, C.c_double) if want_H else None, int(sum_float), C.byref(nc))
+    return e, H.reshape(6, 6).T.copy(), b, nc.value
+
+
+def register_ndt(target, source, res=1.0, mode=D2D, method=DIRECT7, radius=-1.0, guess=None, params=None, accum_double=True):
+    """Whole NDTCuda registration (ndt_cuda_impl.hpp:70-90) with the float oracle."""
+    tm = VoxelMap(target, None, res, accum_double=accum_double)
+    src, src_cov, _keep = _ndt_source(source, res, mode, accum_double)
+    offs = _i32(offsets(method, radius))
+    params = params or default_params()
+    g = _pose_in(np.eye(4) if guess is None else guess)
+    r = LsqResult()
+    lib().orc_align_ndt(tm._h, _p(src, C.c_float), _p(_f32(src_cov), C.c_float) if src_cov is not None else None, len(src), _p(offs, C.c_int), len(offs), C.byref(params),
+                        _p(g, C.c_double), 0, C.byref(r))
     return AlignResult(r)
 
 

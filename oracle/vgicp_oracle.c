@@ -484,7 +484,20 @@ static inline int voxelmap_lookup(const OrcVoxelMap* m, const int* c) {
   return -1;
 }
 
+static OrcVoxelMap* voxelmap_build_impl(const float* pts, const float* cov9, int n, float res, int init_buckets, int max_scan, int accum_double, int ndt);
+
 ORC_API OrcVoxelMap* orc_voxelmap_build(const float* pts, const float* cov9, int n, float res, int init_buckets, int max_scan, int accum_double) {
+  return voxelmap_build_impl(pts, cov9, n, res, init_buckets, max_scan, accum_double, 0);
+}
+
+/* NDT voxel map: GaussianVoxelMap::create_voxelmap(points) gaussian_voxelmap.cu:209-231 -- accumulate p and p p^T
+ * (:122-148), ndt_finalize_voxels_kernel (:178-198): mean = sum/n, cov = (sum_ppT - mean * sum^T)/n, then
+ * covariance_regularization(MIN_EIG) on the voxel covariances (ndt_cuda.cu:129,140). */
+ORC_API OrcVoxelMap* orc_ndt_voxelmap_build(const float* pts, int n, float res, int init_buckets, int max_scan, int accum_double) {
+  return voxelmap_build_impl(pts, NULL, n, res, init_buckets, max_scan, accum_double, 1);
+}
+
+static OrcVoxelMap* voxelmap_build_impl(const float* pts, const float* cov9, int n, float res, int init_buckets, int max_scan, int accum_double, int ndt) {
   OrcVoxelMap* m = (OrcVoxelMap*)calloc(1, sizeof(OrcVoxelMap));
   m->res = res;
   m->max_scan = max_scan;
@@ -542,15 +555,41 @@ ORC_API OrcVoxelMap* orc_voxelmap_build(const float* pts, const float* cov9, int
     int id = voxelmap_lookup(m, coords + 3 * i);
     if (id < 0) continue;
     m->vox_n[id]++;
+    float ppt[9];
+    const float* add9 = cov9 ? cov9 + 9 * (size_t)i : ppt;
+    if (ndt) { /* cov = mean * mean^T of the point, :139 */
+      const float* q = pts + 3 * (size_t)i;
+      for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) ppt[c * 3 + r] = q[r] * q[c];
+    }
     if (accum_double) {
       for (int d = 0; d < 3; d++) dsum[(size_t)id * 12 + d] += (double)pts[3 * (size_t)i + d];
-      for (int d = 0; d < 9; d++) dsum[(size_t)id * 12 + 3 + d] += (double)cov9[9 * (size_t)i + d];
+      if (ndt) { /* the CUDA path forms p p^T in double before adding */
+        const float* q = pts + 3 * (size_t)i;
+        for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) dsum[(size_t)id * 12 + 3 + c * 3 + r] += (double)q[r] * (double)q[c];
+      } else {
+        for (int d = 0; d < 9; d++) dsum[(size_t)id * 12 + 3 + d] += (double)add9[d];
+      }
     } else {
       for (int d = 0; d < 3; d++) m->vox_mean[(size_t)id * 3 + d] += pts[3 * (size_t)i + d];
-      for (int d = 0; d < 9; d++) m->vox_cov[(size_t)id * 9 + d] += cov9[9 * (size_t)i + d];
+      for (int d = 0; d < 9; d++) m->vox_cov[(size_t)id * 9 + d] += add9[d];
     }
   }
-  for (int v = 0; v < V; v++) { /* finalize_voxels_kernel :158-176 */
+  for (int v = 0; v < V; v++) { /* finalize_voxels_kernel :158-176 / ndt_finalize_voxels_kernel :178-198 */
+    if (ndt) {
+      if (accum_double) {
+        double nn = (double)m->vox_n[v], mean[3];
+        for (int d = 0; d < 3; d++) mean[d] = dsum[(size_t)v * 12 + d] / nn;
+        for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++)
+          m->vox_cov[(size_t)v * 9 + c * 3 + r] = (float)((dsum[(size_t)v * 12 + 3 + c * 3 + r] - mean[r] * dsum[(size_t)v * 12 + c]) / nn);
+        for (int d = 0; d < 3; d++) m->vox_mean[(size_t)v * 3 + d] = (float)mean[d];
+      } else {
+        float nn = (float)m->vox_n[v], sum[3], mean[3];
+        for (int d = 0; d < 3; d++) { sum[d] = m->vox_mean[(size_t)v * 3 + d]; mean[d] = sum[d] / nn; }
+        for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) m->vox_cov[(size_t)v * 9 + c * 3 + r] = (m->vox_cov[(size_t)v * 9 + c * 3 + r] - mean[r] * sum[c]) / nn;
+        for (int d = 0; d < 3; d++) m->vox_mean[(size_t)v * 3 + d] = mean[d];
+      }
+      continue;
+    }
     if (accum_double) {
       double nn = (double)m->vox_n[v];
       for (int d = 0; d < 3; d++) m->vox_mean[(size_t)v * 3 + d] = (float)(dsum[(size_t)v * 12 + d] / nn);
@@ -563,6 +602,7 @@ ORC_API OrcVoxelMap* orc_voxelmap_build(const float* pts, const float* cov9, int
   }
   free(dsum);
   free(coords);
+  if (ndt) orc_regularize(m->vox_cov, V, ORC_REG_MIN_EIG); /* ndt_cuda.cu:129,140 */
   return m;
 }
 
@@ -642,8 +682,24 @@ ORC_API long orc_find_correspondences(const OrcVoxelMap* m, const float* src, in
  *     unspecified, the two bracket it.
  *     H36 column-major 6x6, b6; returns the error.
  * ---------------------------------------------------------------------------------------------------------- */
+static double compute_derivatives_impl(const OrcVoxelMap* m, const float* src, const float* src_cov9, const int* pairs, long n_pairs, const float* Tlin, const float* Teval,
+                                       double* H36, double* b6, int sum_float, int ndt);
+
 ORC_API double orc_compute_derivatives(const OrcVoxelMap* m, const float* src, const float* src_cov9, const int* pairs, long n_pairs, const float* Tlin, const float* Teval,
                                        double* H36, double* b6, int sum_float) {
+  return compute_derivatives_impl(m, src, src_cov9, pairs, n_pairs, Tlin, Teval, H36, b6, sum_float, 0);
+}
+
+/* NDT: ndt_compute_derivatives.cu:33-175.  src_cov9 == NULL: P2D (M = cov_B^-1, :73); else D2D (M = (cov_B + R C_A R^T)^-1, :146).
+ * weight = cauchy(resolution, |e|) (:15-18,78,150); voxels with <= 6 points contribute nothing (:61,132), also in the
+ * error-only call (the reference evaluates the same functor and drops H, b). */
+ORC_API double orc_ndt_compute_derivatives(const OrcVoxelMap* m, const float* src, const float* src_cov9, const int* pairs, long n_pairs, const float* Tlin, const float* Teval,
+                                           double* H36, double* b6, int sum_float) {
+  return compute_derivatives_impl(m, src, src_cov9, pairs, n_pairs, Tlin, Teval, H36, b6, sum_float, 1);
+}
+
+static double compute_derivatives_impl(const OrcVoxelMap* m, const float* src, const float* src_cov9, const int* pairs, long n_pairs, const float* Tlin, const float* Teval,
+                                       double* H36, double* b6, int sum_float, int ndt) {
   double Hd[36] = {0}, bd[6] = {0}, ed = 0.0;
   float Hf[36] = {0}, bf[6] = {0}, ef = 0.0f;
   int want = (H36 != NULL && b6 != NULL);
@@ -653,9 +709,11 @@ ORC_API double orc_compute_derivatives(const OrcVoxelMap* m, const float* src, c
     int ia = pairs[2 * ci], iv = pairs[2 * ci + 1];
     if (iv < 0) continue;
     int np = m->vox_n[iv];
-    if (want && np <= 0) continue; /* :62-64 (the error-only functor has no such guard, :105-135) */
+    if (!ndt && want && np <= 0) continue; /* :62-64 (the error-only functor has no such guard, :105-135) */
+    if (ndt && np <= 6) continue;
     const float* meanA = src + 3 * (size_t)ia;
-    const float* covA = src_cov9 + 9 * (size_t)ia;
+    static const float zero9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const float* covA = src_cov9 ? src_cov9 + 9 * (size_t)ia : zero9;
     const float* meanB = m->vox_mean + 3 * (size_t)iv;
     const float* covB = m->vox_cov + 9 * (size_t)iv;
     float pa[3];
@@ -665,8 +723,15 @@ ORC_API double orc_compute_derivatives(const OrcVoxelMap* m, const float* src, c
     mul3f(tmp, Rlt, RCR);
     for (int j = 0; j < 9; j++) S[j] = covB[j] + RCR[j];
     inv3f(S, Minv);
-    float w = sqrtf((float)np);
     float e[3] = {meanB[0] - pa[0], meanB[1] - pa[1], meanB[2] - pa[2]};
+    float w;
+    if (ndt) {
+      float x = sqrtf((e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]); /* error.norm() */
+      float k_sq = m->res * m->res;
+      w = k_sq / (k_sq + x * x);
+    } else {
+      w = sqrtf((float)np);
+    }
     float Me[3];
     for (int r = 0; r < 3; r++) Me[r] = (M3(Minv, r, 0) * e[0] + M3(Minv, r, 1) * e[1]) + M3(Minv, r, 2) * e[2];
     float err = w * ((e[0] * Me[0] + e[1] * Me[1]) + e[2] * Me[2]);
@@ -890,6 +955,7 @@ typedef struct {
   const int* offsets;
   int n_off;
   int sum_float;
+  int ndt;
   float Tlin[16];
   int* pairs;
   long n_pairs, cap_pairs;
@@ -903,13 +969,13 @@ static double f32_linearize(void* c, const double* T, double* H, double* b) {
   p->n_pairs = orc_find_correspondences(p->map, p->src, p->n_src, p->Tlin, p->offsets, p->n_off, p->pairs, p->cap_pairs);
   float Te[16];
   to_f32_pose(T, Te);
-  return orc_compute_derivatives(p->map, p->src, p->src_cov9, p->pairs, p->n_pairs, p->Tlin, Te, H, b, p->sum_float);
+  return compute_derivatives_impl(p->map, p->src, p->src_cov9, p->pairs, p->n_pairs, p->Tlin, Te, H, b, p->sum_float, p->ndt);
 }
 static double f32_error(void* c, const double* T) {
   F32Problem* p = (F32Problem*)c;
   float Te[16];
   to_f32_pose(T, Te);
-  return orc_compute_derivatives(p->map, p->src, p->src_cov9, p->pairs, p->n_pairs, p->Tlin, Te, NULL, NULL, p->sum_float);
+  return compute_derivatives_impl(p->map, p->src, p->src_cov9, p->pairs, p->n_pairs, p->Tlin, Te, NULL, NULL, p->sum_float, p->ndt);
 }
 
 /* align(): LsqRegistration::computeTransformation with the float problem; guess/T 4x4 col-major double */
@@ -923,6 +989,33 @@ ORC_API int orc_align_f32(const OrcVoxelMap* map, const float* src, const float*
   lsq_optimize(params, &p, f32_linearize, f32_error, guess, res);
   free(p.pairs);
   return 0;
+}
+
+/* NDTCuda::align (ndt_cuda_impl.hpp:70-90): src = source points (P2D, src_cov9 NULL) or source voxel means + covariances (D2D) */
+ORC_API int orc_align_ndt(const OrcVoxelMap* map, const float* src, const float* src_cov9, int n_src, const int* offsets, int n_off, const OrcLsqParams* params,
+                          const double* guess, int sum_float, OrcLsqResult* res) {
+  F32Problem p;
+  memset(&p, 0, sizeof(p));
+  p.map = map; p.src = src; p.src_cov9 = src_cov9; p.n_src = n_src; p.offsets = offsets; p.n_off = n_off; p.sum_float = sum_float; p.ndt = 1;
+  p.cap_pairs = (long)n_src * n_off;
+  p.pairs = (int*)malloc(sizeof(int) * 2 * (size_t)(p.cap_pairs > 0 ? p.cap_pairs : 1));
+  lsq_optimize(params, &p, f32_linearize, f32_error, guess, res);
+  free(p.pairs);
+  return 0;
+}
+
+ORC_API double orc_evaluate_ndt(const OrcVoxelMap* map, const float* src, const float* src_cov9, int n_src, const int* offsets, int n_off, const double* Tlin_d,
+                                const double* Teval_d, double* H36, double* b6, int sum_float, long* n_corr) {
+  float Tl[16], Te[16];
+  to_f32_pose(Tlin_d, Tl);
+  to_f32_pose(Teval_d, Te);
+  long cap = (long)n_src * n_off;
+  int* pairs = (int*)malloc(sizeof(int) * 2 * (size_t)(cap > 0 ? cap : 1));
+  long np = orc_find_correspondences(map, src, n_src, Tl, offsets, n_off, pairs, cap);
+  double e = orc_ndt_compute_derivatives(map, src, src_cov9, pairs, np, Tl, Te, H36, b6, sum_float);
+  if (n_corr) *n_corr = np;
+  free(pairs);
+  return e;
 }
 
 /* one evaluation, for stage-level tests: update_correspondences(Tlin) + compute_error(Teval,H,b) */

@@ -24,7 +24,7 @@ def _pygicp():
 def test_pygicp_surface():
     """Same module-level names and method names as the reference binding (main.cpp:145-217) for the accelerated path."""
     m = _pygicp()
-    for name in ("downsample", "align_points", "LsqRegistration", "FastVGICPCuda"):
+    for name in ("downsample", "align_points", "LsqRegistration", "FastVGICPCuda", "NDTCuda"):
         assert hasattr(m, name), name
     for meth in ("set_input_target", "set_input_source", "swap_source_and_target", "get_final_hessian", "get_final_transformation", "align",
                  "set_resolution", "set_neighbor_search_method", "set_correspondence_randomness", "get_fitness_score"):
@@ -61,6 +61,23 @@ def test_cpp_alignment_test_binary(pair02, tmp_path):
                           os.path.join(ROOT, "tests", "golden", "relative.txt")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "PASSED" in out.stdout
+
+
+@pytest.mark.gpu
+def test_pygicp_ndt(pair02, relative_pose):
+    m = _pygicp()
+    tgt, src = pair02
+    T = m.align_points(tgt.astype(np.float64), src.astype(np.float64), method="NDT_CUDA", neighbor_search_method="DIRECT7")
+    e = pose_error(relative_pose, T)
+    assert e[0] < 0.05 and e[1] < np.radians(1.0)
+    reg = m.NDTCuda()
+    reg.set_resolution(1.0)
+    reg.set_neighbor_search_method("DIRECT7", 0.0)
+    reg.set_input_target(tgt.astype(np.float64))
+    reg.set_input_source(src.astype(np.float64))
+    T2 = reg.align()
+    e = pose_error(relative_pose, T2)
+    assert reg.has_converged() and e[0] < 0.05 and e[1] < np.radians(1.0)
 
 
 @pytest.mark.gpu

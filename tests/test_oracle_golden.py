@@ -152,3 +152,30 @@ def test_voxelmap_invariants(pair02, covs):
     sel = (coords == coords[0]).all(axis=1)
     assert d[key][0] == sel.sum()
     assert np.abs(d[key][1] - tgt[sel].mean(axis=0)).max() < 1e-4
+
+
+@pytest.mark.parametrize("mode,method", [(O.D2D, O.DIRECT7), (O.D2D, O.DIRECT1), (O.P2D, O.DIRECT1)])
+def test_oracle_ndt_reference_gate(pair02, relative_pose, mode, method):
+    """NDT_CUDA rows of gicp_test.cpp (defaults D2D + DIRECT7, ndt_cuda.cu:21-22): 0.05 m / 1 deg / hasConverged on the NDT oracle."""
+    tgt, src = pair02
+    fwd = O.register_ndt(tgt, src, mode=mode, method=method)
+    e = pose_error(relative_pose, fwd.T)
+    assert fwd.converged and e[0] < T_TOL and e[1] < R_TOL, e
+    bwd = O.register_ndt(src, tgt, mode=mode, method=method)
+    e = pose_error(relative_pose, np.linalg.inv(bwd.T))
+    assert bwd.converged and e[0] < T_TOL and e[1] < R_TOL, e
+
+
+def test_oracle_ndt_voxel_covariances_min_eig(pair02):
+    tgt, _ = pair02
+    vm = O.VoxelMap(tgt, None, 1.0, accum_double=True)
+    w = np.linalg.eigvalsh(0.5 * (vm.vox_cov.reshape(-1, 3, 3) + vm.vox_cov.reshape(-1, 3, 3).transpose(0, 2, 1)).astype(np.float64))
+    assert w.min() > 0.99e-3
+    # a populated voxel: covariance equals the sample covariance of its points (population normalisation, :196)
+    coords = O.voxel_coords(tgt, 1.0)
+    v = int(np.argmax(vm.vox_n))
+    b = int(np.flatnonzero(vm.bucket_id == v)[0])
+    sel = (coords == vm.bucket_coord[b]).all(axis=1)
+    P = tgt[sel].astype(np.float64)
+    want = np.cov(P.T, bias=True)
+    assert np.abs(vm.vox_cov[v].reshape(3, 3) - want).max() < 1e-3
