@@ -57,6 +57,10 @@ def load_workload(name):
     if name == "c3":
         t, s, _ = kitti_like_pair(beams=64, az_steps=2083, seed=42, pose=(0.8, 0.05, 0.7), downsample=0.25)
         return dict(name="C3: synthetic HDL-64 pair (0.25 m downsample) DIRECT27 res=1.0", target=t, source=s, method="DIRECT27", res=1.0, data="synthetic")
+    if name == "c5":
+        t, s, _ = kitti_like_pair(beams=64, az_steps=2083, seed=1000, pose=(0.8, 0.05, 0.7), downsample=0.25)
+        return dict(name="C5: NDTCuda D2D DIRECT7 res=1.0, synthetic HDL-64 pair (0.25 m downsample)", target=t, source=s, method="DIRECT7", res=1.0, data="synthetic",
+                    problem="ndt_d2d")
     if name == "c4":
         t, s, _ = kitti_like_pair(beams=128, az_steps=8192, seed=44, pose=(0.5, 0.0, 1.0), downsample=0.0, max_points=1_000_000)
         return dict(name="C4: synthetic 1M-pt pair DIRECT27 res=0.5", target=t, source=s, method="DIRECT27", res=0.5, data="synthetic")
@@ -115,6 +119,8 @@ def cpu_one_registration(w, offs, threads):
     import oracle as O
 
     tgt, src = w["target"], w["source"]
+    if w.get("problem") == "ndt_d2d":  # the reference has no CPU NDT of its own: the float restatement of NDTCuda serves as the CPU arm
+        return O.register_ndt(tgt, src, res=w["res"], mode=O.D2D, method=getattr(O, w["method"]))
     tc = O.covariances_f64(tgt, 20, O.REG_PLANE, threads)
     sc = O.covariances_f64(src, 20, O.REG_PLANE, threads)
     return O.align_f64(tgt, tc, src, sc, res=w["res"], offs=offs, threads=threads)
@@ -215,7 +221,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    from fast_gicp_b200 import FastVGICPCuda
+    from fast_gicp_b200 import FastVGICPCuda, NDTCuda
     from fast_gicp_b200 import distributed as D
     from fast_gicp_b200.core import REG_PLANE, Core, pose_from_c
 
@@ -260,8 +266,15 @@ def main():
     import threading
 
     note("input pool ready (%d pairs)" % P)
+    ndt = w.get("problem") == "ndt_d2d"
     cores = [Core(local_rank) for _ in range(S)]
-    regs = [FastVGICPCuda(local_rank) for _ in range(S)]
+    regs = [(NDTCuda if ndt else FastVGICPCuda)(local_rank) for _ in range(S)]
+    for r in regs:
+        if ndt:
+            r.vgicp_cuda_ = r.ndt_cuda_  # same accessor below
+    for c in cores:
+        if ndt:
+            c.set_problem(2)
     hint = 1 if S > 1 else 0  # many handles share the GPU -> throughput launch shapes (vgicp_set_execution_hint)
     for c in cores:
         c.set_resolution(w["res"])
@@ -270,7 +283,7 @@ def main():
     for r in regs:
         r.setResolution(w["res"])
         r.voxel_resolution_ = w["res"]
-        r.setNeighborSearchMethod(w["method"])
+        r.setNeighborSearchMethod(w["method"], 0.0)
         r.vgicp_cuda_.set_execution_hint(hint)
     core = cores[0]
     streams = [torch.cuda.ExternalStream(c.stream(), device=dev) for c in cores]
@@ -281,6 +294,11 @@ def main():
     def step_resident(ci=0, pi=0):
         """One registration with both clouds resident in HBM: the C-ABI call sequence of setInputTarget + setInputSource + align."""
         c = cores[ci]
+        if ndt:  # NDTCuda: setInputTarget + setInputSource + align (voxel maps from the raw points inside align)
+            c.set_cloud_device("target", tp + pi * n_t * 12, n_t, 12)
+            c.set_cloud_device("source", sp + pi * n_s * 12, n_s, 12)
+            c.ndt_create_voxelmaps()
+            return c.align()
         c.set_cloud_device("target", tp + pi * n_t * 12, n_t, 12)
         c.find_target_neighbors(20)
         c.calculate_target_covariances(REG_PLANE)
@@ -401,6 +419,10 @@ def main():
         peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
     V, B = core.num_voxels(), core.num_buckets()
     # algorithmic bytes per launch, SURVEY.md 8(d)
+    if ndt:
+        METRIC_NAME = "registrations/sec (NDT D2D, KITTI-shaped pairs)"
+    else:
+        METRIC_NAME = METRIC
     alg_bytes = {
         "knn": 52.0 * 0.5 * (n_t + n_s),                    # stage 1 (kNN+cov+reg) 52 B/pt, one cloud per launch
         "covariance": 52.0 * 0.5 * (n_t + n_s),
@@ -439,7 +461,7 @@ def main():
     h2d = (n_t + n_s) * 12
     d2h = n_s * 12 + 16 * 4 + (res.n_linearize * 43 + res.n_compute_error) * 8
     line = {
-        "metric": METRIC, "value": world * S * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC_NAME, "value": world * S * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": w["data"],
         "config": {"workload": w["name"], "protocol": "align.cpp 100times (covariances recomputed every registration)", "step": "one registration on each of the %d concurrent streams of a GPU (one host thread + one handle per stream)" % S,
                    "streams_per_gpu": S, "registrations_per_step": S * world, "execution_hint": "throughput" if hint else "latency",
