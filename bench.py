@@ -430,18 +430,35 @@ def main():
         "linearize": 52.0 * n_s + 52.0 * V + 16.0 * B,       # stage 3, one LM evaluation
         "compute_error": 52.0 * n_s + 52.0 * V + 16.0 * B,
     }
-    dom = max((k for k in per_kernel if k in alg_bytes), key=lambda k: per_kernel[k]["ms_per_step"])
-    pk = per_kernel[dom]
-    launches_dom = pk["launches_per_step"] / (7.0 if dom == "voxelmap_build" else 1.0)  # the build is ~7 small kernels: treat as one unit
-    avg_ms = pk["ms_per_step"] / max(launches_dom, 1e-9)
-    achieved = alg_bytes[dom] / (avg_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
-                "peak_source": peak_src, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes[dom],
-                "kernel_share_of_step": pk["ms_per_step"] / (sum(v["ms_per_step"] for v in per_kernel.values()) or 1.0)}
+    # kernel groups as they appear in the ncu launch list: the evaluation kernel k_linearize<MODE,WANT_H,G> (linearize and
+    # error-only calls are the same template), the k-NN stage (grid build + k_knn_grid + k_knn_grid_heavy), ...
+    groups = {"evaluate (k_linearize, H and error-only)": ["linearize", "compute_error"], "knn stage (k_grid_* + k_knn_grid + k_knn_grid_heavy)": ["knn"],
+              "covariance (k_covariance_knn)": ["covariance"], "voxelmap_build (7 kernels)": ["voxelmap_build"]}
+    total_kernel_ms = sum(v["ms_per_step"] for v in per_kernel.values()) or 1.0
+
+    def group_roofline(gname):
+        cats = [c for c in groups[gname] if c in per_kernel]
+        ms = sum(per_kernel[c]["ms_per_step"] for c in cats)
+        launches_g = sum(per_kernel[c]["launches_per_step"] for c in cats) / (7.0 if "voxelmap" in gname else 1.0)
+        avg_ms = ms / max(launches_g, 1e-9)
+        ab = alg_bytes[cats[0]]
+        ach = ab / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            vals = [tj[c] for c in cats if c in tj]
+            traffic = float(np.mean(vals)) if vals else None
+        return {"bound": "hbm", "kernel": gname, "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": ab, "kernel_share_of_step": ms / total_kernel_ms}
+
+    present = [g for g in groups if any(c in per_kernel for c in groups[g])]
+    rl = {g: group_roofline(g) for g in present}
+    dom = max(present, key=lambda g: rl[g]["kernel_share_of_step"])
+    roofline = rl[dom]
+    roofline["note"] = ("at ~17k points every kernel is latency/issue-bound (one evaluation moves ~1 MB = 0.17 us at the HBM peak); the fraction is reported as the "
+                        "contract asks, the 1M-point numbers are in profiles/README.md")
+    roofline_other = {g: {k: rl[g][k] for k in ("achieved", "frac", "avg_launch_ms", "kernel_share_of_step", "algorithmic_bytes_per_launch", "traffic")} for g in present if g != dom}
 
     note("profile pass done")
     cpu_baseline = None
@@ -471,7 +488,7 @@ def main():
         "e2e": {"value": world * S * K / (total_ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * S, "d2h_bytes_per_step": d2h * S, "ms_per_step": total_ms_e2e / K,
                 "api": "FastVGICPCuda.setInputTarget/setInputSource/align (pinned host buffers, aligned cloud + pose read back)"},
         "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "per_kernel": per_kernel,
+        "roofline": roofline, "roofline_other_kernels": roofline_other, "cpu_baseline": cpu_baseline, "clocks": clocks, "per_kernel": per_kernel,
         "single_stream": {"ms_per_registration": float(np.mean(lat)), "registrations_per_s": 1e3 / float(np.mean(lat)),
                           "e2e_ms_per_registration": float(np.mean(lat_e2e)), "e2e_registrations_per_s": 1e3 / float(np.mean(lat_e2e)),
                           "l2": "flushed between registrations (256 MiB memset)", "protocol": "sequential, as src/align.cpp:72-81"},
