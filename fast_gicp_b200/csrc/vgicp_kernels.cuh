@@ -403,7 +403,11 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl,
   for (int i = 0; i < NV; i++) sum[i] = 0.f;
   const int n_off = MODE == 0 ? a.n_off : NOFF;
   const long long n_tasks = (long long)a.n * G;
-  for (long long task = (long long)blockIdx.x * kLinThreads + threadIdx.x; task < n_tasks; task += (long long)gridDim.x * kLinThreads) {
+  // warp-uniform trip count (the body uses warp votes): lanes past the end are clamped onto the last task and masked out
+  for (long long base = (long long)blockIdx.x * kLinThreads + (threadIdx.x & ~31); base < n_tasks; base += (long long)gridDim.x * kLinThreads) {
+    const long long task_raw = base + (threadIdx.x & 31);
+    const bool active = task_raw < n_tasks;
+    const long long task = active ? task_raw : n_tasks - 1;
     const int i = (int)(task / G);
     const int sub = (int)(task % G);
     float4 p = a.pts[i];
@@ -442,7 +446,8 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl,
 #pragma unroll
       for (int d = 0; d < 3; d++) kzm[d] = hash_mix((uint64_t)(int64_t)(bz + d - 1));
     }
-    for (int o0 = sub; o0 < n_off; o0 += G * CELLS) {
+    for (int o_base = 0; o_base < n_off; o_base += G * CELLS) {  // same trip count in every lane (warp votes below)
+      const int o0 = o_base + sub;
       // phase 1: all first-probe bucket loads of this lane in flight together
       int cx[CELLS], cy[CELLS], cz[CELLS];
       unsigned pos[CELLS];
@@ -456,7 +461,7 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl,
 #pragma unroll
       for (int j = 0; j < CELLS; j++) {
         const int o = o0 + j * G;
-        valid[j] = o < n_off;
+        valid[j] = active && o < n_off;
         int3 off;
         if (MODE == 0) {
           int4 t4 = __ldg(&a.offsets[valid[j] ? o : 0]);
@@ -483,11 +488,19 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl,
           if (s + 1 < a.max_scan) b = __ldg(&a.buckets[pos[j]]);
         }
         id[j] = valid[j] ? found : -1;
-        const float4* vr = reinterpret_cast<const float4*>(a.vox + (id[j] >= 0 ? id[j] : 0));
-        mn[j] = __ldg(vr); c0[j] = __ldg(vr + 1); c1[j] = __ldg(vr + 2);
+        // voxel record: three 16-byte loads, predicated per lane (a miss needs no data), all issued before any of the math below
+        mn[j] = c0[j] = c1[j] = make_float4(0.f, 0.f, 0.f, 1.f);
+        if (id[j] >= 0) {
+          const float4* vr = reinterpret_cast<const float4*>(a.vox + id[j]);
+          mn[j] = __ldg(vr); c0[j] = __ldg(vr + 1); c1[j] = __ldg(vr + 2);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < CELLS; j++) accumulate_voxel<WANT_H>(mn[j], c0[j], c1[j], id[j] >= 0, rcr, pe, acc, a.ndt, a.res);
+      for (int j = 0; j < CELLS; j++) {
+        // neighbouring points see the same empty cells (above/below a surface): when no lane of the warp hit this cell, the
+        // 3x3 inversion and the accumulation are skipped for the whole warp
+        if (__any_sync(0xffffffffu, id[j] >= 0)) accumulate_voxel<WANT_H>(mn[j], c0[j], c1[j], id[j] >= 0, rcr, pe, acc, a.ndt, a.res);
+      }
     }
 
     if (WANT_H) {
