@@ -510,7 +510,7 @@ __device__ __forceinline__ void topk_merge32(WarpTopK& t, int k, int lane, tkey 
       cmpx(c, stride, lower == up);
     }
   }
-  if (t.e0 == kKeyInf && __all_sync(0xffffffffu, t.e0 == kKeyInf)) {
+  if (__all_sync(0xffffffffu, t.e0 == kKeyInf)) {  // (the vote must not sit behind a per-lane short-circuit)
     t.e0 = c;  // empty list: the sorted batch is the list
   } else {
     tkey r = __shfl_sync(0xffffffffu, c, 31 - lane);
@@ -522,10 +522,12 @@ __device__ __forceinline__ void topk_merge32(WarpTopK& t, int k, int lane, tkey 
 }
 
 // all 32 lanes call this with their candidate (valid=false for padding lanes)
+// `bound`: an upper bound on the k-th smallest key known from a previous (smaller) block -- candidates above it cannot be among
+// the k nearest and are dropped before they cost a merge
 template <bool WIDE>
-__device__ __forceinline__ void topk_offer(WarpTopK& t, int k, int lane, bool valid, float cd, int ci) {
+__device__ __forceinline__ void topk_offer(WarpTopK& t, int k, int lane, bool valid, float cd, int ci, tkey bound = kKeyInf) {
   const tkey c = make_key(cd, ci);
-  const bool pass = valid && c < t.worst;
+  const bool pass = valid && c < t.worst && c <= bound;
   unsigned m = __ballot_sync(0xffffffffu, pass);
   if (!WIDE && __popc(m) > 3) {  // many entrants: one sort-merge instead of one insertion each
     topk_merge32(t, k, lane, pass ? c : kKeyInf);
@@ -568,7 +570,7 @@ __device__ __forceinline__ float knn_d2(float4 q, float4 t) {  // (dx*dx + dy*dy
 
 // scan one contiguous run of the cell-sorted array (whole-cloud fallback), four loads in flight
 template <bool WIDE>
-__device__ __forceinline__ void scan_run(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int start, int count) {
+__device__ __forceinline__ void scan_run(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int start, int count, tkey bound = kKeyInf) {
   constexpr int U = 4;
   for (int off = 0; off < count; off += 32 * U) {
     float4 c[U];
@@ -581,7 +583,7 @@ __device__ __forceinline__ void scan_run(WarpTopK& t, int k, int lane, float4 q,
     }
 #pragma unroll
     for (int u = 0; u < U; u++)
-      if (off + u * 32 < count) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w));
+      if (off + u * 32 < count) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w), bound);
   }
 }
 
@@ -605,7 +607,7 @@ __device__ __forceinline__ void probe_cell(const GridLevel& lv, unsigned tmask, 
 // values.  Four batches (loads) are kept in flight: a sparse query can own thousands of candidates and a single warp
 // is latency-bound.
 template <bool WIDE>
-__device__ __forceinline__ void scan_lane_cells(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int my_start, int my_count) {
+__device__ __forceinline__ void scan_lane_cells(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int my_start, int my_count, tkey bound = kKeyInf) {
   int incl = my_count;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -637,14 +639,15 @@ __device__ __forceinline__ void scan_lane_cells(WarpTopK& t, int k, int lane, fl
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      if (base + u * 32 < total) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w));
+      if (base + u * 32 < total) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w), bound);
     }
   }
 }
 
 // the same scans with the batches dealt round-robin to `nw` cooperating warps (warp `wi` takes batches wi, wi+nw, ...)
 template <bool WIDE>
-__device__ __forceinline__ void scan_lane_cells_strided(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int my_start, int my_count, int wi, int nw) {
+__device__ __forceinline__ void scan_lane_cells_strided(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int my_start, int my_count, int wi, int nw,
+                                                        tkey bound = kKeyInf) {
   int incl = my_count;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -677,12 +680,12 @@ __device__ __forceinline__ void scan_lane_cells_strided(WarpTopK& t, int k, int 
     }
 #pragma unroll
     for (int u = 0; u < U; u++)
-      if (base + u * 32 * nw < total) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w));
+      if (base + u * 32 * nw < total) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w), bound);
   }
 }
 
 template <bool WIDE>
-__device__ __forceinline__ void scan_run_strided(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int start, int count, int wi, int nw) {
+__device__ __forceinline__ void scan_run_strided(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int start, int count, int wi, int nw, tkey bound = kKeyInf) {
   constexpr int U = 4;
   for (int off = wi * 32; off < count; off += 32 * U * nw) {
     float4 c[U];
@@ -695,7 +698,7 @@ __device__ __forceinline__ void scan_run_strided(WarpTopK& t, int k, int lane, f
     }
 #pragma unroll
     for (int u = 0; u < U; u++)
-      if (off + u * 32 * nw < count) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w));
+      if (off + u * 32 * nw < count) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w), bound);
   }
 }
 
@@ -728,9 +731,14 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid(GridArgs a, int
     WarpTopK t;
     topk_reset(t);
     bool done = false, deferred = false;
+    tkey bound = kKeyInf;  // k-th key of the last block that failed to certify: an upper bound on the true k-th key
     if (!force_bruteforce) {
       for (int l = 0; l < a.L && !done; l++) {
         const float s = grid_cell_size(g, l, a.L);
+        if (bound != kKeyInf) {  // a level whose certificate radius is below the known lower bound s_prev cannot help; one that covers
+          const float need = sqrtf(__uint_as_float((unsigned)(bound >> 32)));  // the upper bound certifies for sure: skip in between
+          if (l + 1 < a.L && s * 0.999f < need && grid_cell_size(g, l + 1, a.L) * 0.999f <= need) continue;
+        }
         const float inv_s = 1.0f / s;
         const GridLevel lv = a.lv[l];
         int3 c = grid_cell(g, inv_s, q.x, q.y, q.z);
@@ -748,9 +756,10 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid(GridArgs a, int
           break;
         }
         topk_reset(t);
-        scan_lane_cells<WIDE>(t, k, lane, q, lv.sorted, st, cn);
+        scan_lane_cells<WIDE>(t, k, lane, q, lv.sorted, st, cn, bound);
         const float r1 = s * 0.999f;
         if (topk_worst_d2(t) <= r1 * r1) { done = true; break; }  // every point within s of q lies inside the 3x3x3 block
+        if (t.worst != kKeyInf) bound = t.worst;
       }
     }
     if (deferred) continue;
@@ -773,6 +782,7 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid_heavy(GridArgs 
   __shared__ tkey se[kKnnGridWarps][64];
   __shared__ int s_next;
   __shared__ int s_done;
+  __shared__ tkey s_bound;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int k = a.k;
   GridGeom g = grid_geom(a.bbox_min, a.bbox_max);
@@ -792,11 +802,16 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid_heavy(GridArgs 
     float4 q = __ldg(&a.lv[0].sorted[item.x]);
     const int qi = __float_as_int(q.w);
     WarpTopK t;
+    tkey bound = kKeyInf;
     for (int l = item.y; l <= a.L; l++) {
       topk_reset(t);
       float s = 0.f;
       if (l < a.L) {
         s = grid_cell_size(g, l, a.L);
+        if (bound != kKeyInf) {
+          const float need = sqrtf(__uint_as_float((unsigned)(bound >> 32)));
+          if (l + 1 < a.L && s * 0.999f < need && grid_cell_size(g, l + 1, a.L) * 0.999f <= need) continue;  // identical in all warps
+        }
         const float inv_s = 1.0f / s;
         const GridLevel lv = a.lv[l];
         int3 c = grid_cell(g, inv_s, q.x, q.y, q.z);
@@ -806,9 +821,9 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid_heavy(GridArgs 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
         if (total < k) continue;  // warp-uniform and identical in all warps
-        scan_lane_cells_strided<WIDE>(t, k, lane, q, lv.sorted, st, cn, wid, kKnnGridWarps);
+        scan_lane_cells_strided<WIDE>(t, k, lane, q, lv.sorted, st, cn, wid, kKnnGridWarps, bound);
       } else {
-        scan_run_strided<WIDE>(t, k, lane, q, a.lv[0].sorted, 0, a.n, wid, kKnnGridWarps);
+        scan_run_strided<WIDE>(t, k, lane, q, a.lv[0].sorted, 0, a.n, wid, kKnnGridWarps, bound);
       }
       // merge the per-warp lists in warp 0
       se[wid][lane] = t.e0;
@@ -830,10 +845,11 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid_heavy(GridArgs 
           if (lane < k) row[lane] = key_index(t.e0);
           if (WIDE && 32 + lane < k) row[32 + lane] = key_index(t.e1);
         }
-        if (lane == 0) s_done = ok ? 1 : 0;
+        if (lane == 0) { s_done = ok ? 1 : 0; s_bound = t.worst; }
       }
       __syncthreads();
       if (s_done) break;
+      if (s_bound != kKeyInf) bound = s_bound;
     }
   }
 }
