@@ -590,7 +590,7 @@ __device__ __forceinline__ void scan_run(WarpTopK& t, int k, int lane, float4 q,
 __device__ __forceinline__ void probe_cell(const GridLevel& lv, unsigned tmask, int x, int y, int z, int& start, int& count) {
   count = 0;
   start = 0;
-  if (x < -1 || y < -1 || z < -1) return;
+  if (x < 0 || y < 0 || z < 0) return;  // no point lies below the bounding-box minimum
   unsigned long long key = grid_key(x, y, z);
   unsigned pos = grid_hash(key) & tmask;
   for (;;) {
@@ -702,6 +702,34 @@ __device__ __forceinline__ void scan_run_strided(WarpTopK& t, int k, int lane, f
   }
 }
 
+// Extension step.  The 3x3x3 block of a level held >= k points, but its k-th distance B exceeds the certificate radius s.  Every
+// true neighbour lies within B of q, and while B <= 2 s that ball is inside the 5x5x5 block around q's cell: merging the shell
+// cells (5^3 minus the 3^3 already merged) that intersect the ball completes the answer exactly.  On LiDAR surfaces that is a
+// handful of points, against the ~4x larger block of the next coarser level a restart would scan.
+template <bool WIDE>
+__device__ __forceinline__ bool extend_shell(WarpTopK& t, int k, int lane, float4 q, const GridGeom& g, float s, const GridLevel& lv, unsigned tmask, int3 c) {
+  const float B = sqrtf(topk_worst_d2(t));
+  if (!(B <= 2.f * s * 0.999f)) return false;  // (also rejects an unfilled list)
+  const float reach = B + 1e-3f * s;           // slack for the rounding of the cell boundaries
+  const float reach2 = reach * reach;
+  const float fx = q.x - g.minx, fy = q.y - g.miny, fz = q.z - g.minz;
+  for (int r = 0; r < 4; r++) {
+    const int idx = r * 32 + lane;
+    int st = 0, cn = 0;
+    if (idx < 125) {
+      const int dx = idx / 25 - 2, dy = (idx / 5) % 5 - 2, dz = idx % 5 - 2;
+      if (max(abs(dx), max(abs(dy), abs(dz))) == 2) {
+        const int cx = c.x + dx, cy = c.y + dy, cz = c.z + dz;
+        const float lx = cx * s, ly = cy * s, lz = cz * s;
+        const float ex = fmaxf(fmaxf(lx - fx, fx - (lx + s)), 0.f), ey = fmaxf(fmaxf(ly - fy, fy - (ly + s)), 0.f), ez = fmaxf(fmaxf(lz - fz, fz - (lz + s)), 0.f);
+        if (ex * ex + ey * ey + ez * ez <= reach2) probe_cell(lv, tmask, cx, cy, cz, st, cn);
+      }
+    }
+    if (__any_sync(0xffffffffu, cn > 0)) scan_lane_cells<WIDE>(t, k, lane, q, lv.sorted, st, cn);
+  }
+  return true;
+}
+
 constexpr int kKnnGridWarps = 8;      // warps (queries) per block
 constexpr int kHeavyCandidates = 768; // blocks with more candidates than this go to the block-cooperative kernel
 // nearest-first order of the 3x3x3 block (index = 9*(dx+1) + 3*(dy+1) + (dz+1)): centre, 6 faces, 12 edges, 8 corners
@@ -710,7 +738,7 @@ __constant__ unsigned char kBlockOrder[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5
 // Persistent warps pull queries from a global counter (the cost of a query varies by >10x between dense and sparse
 // regions, and queries are visited in cell order, so static blocks would leave a long tail).
 template <bool WIDE>
-__global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid(GridArgs a, int force_bruteforce) {
+__global__ void __launch_bounds__(kKnnGridWarps * 32, 4) k_knn_grid(GridArgs a, int force_bruteforce) {
   const int lane = threadIdx.x & 31;
   const int k = a.k;
   GridGeom g = grid_geom(a.bbox_min, a.bbox_max);
@@ -759,7 +787,10 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid(GridArgs a, int
         scan_lane_cells<WIDE>(t, k, lane, q, lv.sorted, st, cn, bound);
         const float r1 = s * 0.999f;
         if (topk_worst_d2(t) <= r1 * r1) { done = true; break; }  // every point within s of q lies inside the 3x3x3 block
-        if (t.worst != kKeyInf) bound = t.worst;
+        if (t.worst != kKeyInf) {
+          if (extend_shell<WIDE>(t, k, lane, q, g, s, lv, a.tmask, c)) { done = true; break; }
+          bound = t.worst;
+        }
       }
     }
     if (deferred) continue;
@@ -806,6 +837,8 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid_heavy(GridArgs 
     for (int l = item.y; l <= a.L; l++) {
       topk_reset(t);
       float s = 0.f;
+      GridLevel lv = a.lv[0];
+      int3 c = make_int3(0, 0, 0);
       if (l < a.L) {
         s = grid_cell_size(g, l, a.L);
         if (bound != kKeyInf) {
@@ -813,8 +846,8 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid_heavy(GridArgs 
           if (l + 1 < a.L && s * 0.999f < need && grid_cell_size(g, l + 1, a.L) * 0.999f <= need) continue;  // identical in all warps
         }
         const float inv_s = 1.0f / s;
-        const GridLevel lv = a.lv[l];
-        int3 c = grid_cell(g, inv_s, q.x, q.y, q.z);
+        lv = a.lv[l];
+        c = grid_cell(g, inv_s, q.x, q.y, q.z);
         int st = 0, cn = 0;
         if (lane < 27) probe_cell(lv, a.tmask, c.x + dx, c.y + dy, c.z + dz, st, cn);
         int total = cn;
@@ -839,7 +872,8 @@ __global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid_heavy(GridArgs 
           }
         }
         const float r1 = s * 0.999f;
-        const bool ok = (l == a.L) || (topk_worst_d2(t) <= r1 * r1);
+        bool ok = (l == a.L) || (topk_worst_d2(t) <= r1 * r1);
+        if (!ok && t.worst != kKeyInf) ok = extend_shell<WIDE>(t, k, lane, q, g, s, lv, a.tmask, c);
         if (ok) {
           int* row = a.nbr + (size_t)qi * k;
           if (lane < k) row[lane] = key_index(t.e0);
