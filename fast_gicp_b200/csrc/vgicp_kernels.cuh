@@ -26,7 +26,7 @@
 namespace vgicp {
 
 constexpr int kLinThreads = 128;     // block size of the linearize kernel
-constexpr int kLinMaxBlocks = 592;   // 4 x 148 SMs: upper bound on partial sums the last block has to fold
+constexpr int kLinMaxBlocks = 592;   // 4 x 148 SMs: upper bound on partial sums the last block has to fold (more resident warps only thrash L1: measured)
 constexpr int kLinValues = 28;       // 21 unique H + 6 b + 1 err
 
 struct Pose {      // float image of an Eigen::Isometry3f: R row-major here, t
@@ -99,11 +99,36 @@ __global__ void k_unpack_points(const unsigned char* __restrict__ raw, size_t st
 // is exactly what serial first-come-first-served insertion of the distinct voxels in lexicographic order produces,
 // independent of thread timing -- the order the oracle uses.  slots[] holds a representative point index per voxel.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_voxel_coords(const float4* __restrict__ pts, int n, float res, int4* __restrict__ coords) {
+// bbox[0..2] / bbox[3..5]: running min / max of the voxel coordinates (sizes the direct-mapped index of the evaluation kernels)
+__global__ void k_voxel_coords(const float4* __restrict__ pts, int n, float res, int4* __restrict__ coords, int* __restrict__ bbox) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 p = pts[i];
-  coords[i] = make_int4(voxel_coord1(p.x, res), voxel_coord1(p.y, res), voxel_coord1(p.z, res), 0);
+  int4 c = make_int4(0, 0, 0, 0);
+  const bool in = i < n;
+  if (in) {
+    float4 p = pts[i];
+    c = make_int4(voxel_coord1(p.x, res), voxel_coord1(p.y, res), voxel_coord1(p.z, res), 0);
+    coords[i] = c;
+  }
+  const int lo_x = __reduce_min_sync(0xffffffffu, in ? c.x : INT_MAX), lo_y = __reduce_min_sync(0xffffffffu, in ? c.y : INT_MAX), lo_z = __reduce_min_sync(0xffffffffu, in ? c.z : INT_MAX);
+  const int hi_x = __reduce_max_sync(0xffffffffu, in ? c.x : INT_MIN), hi_y = __reduce_max_sync(0xffffffffu, in ? c.y : INT_MIN), hi_z = __reduce_max_sync(0xffffffffu, in ? c.z : INT_MIN);
+  if ((threadIdx.x & 31) == 0 && lo_x != INT_MAX) {
+    atomicMin(&bbox[0], lo_x); atomicMin(&bbox[1], lo_y); atomicMin(&bbox[2], lo_z);
+    atomicMax(&bbox[3], hi_x); atomicMax(&bbox[4], hi_y); atomicMax(&bbox[5], hi_z);
+  }
+}
+
+// Direct-mapped voxel index: cells[((x - x0) * ny + (y - y0)) * nz + (z - z0)] = voxel id or -1 over the bounding box of the map's
+// voxel coordinates.  A lookup in the reference's table answers "is this coordinate one of the map's voxels, and which" (every stored
+// voxel sits within the probe window of its home bucket and nothing is ever deleted), so any exact index returns the same ids; this
+// one needs no hashing (vector3i_hash is nine 64-bit multiplies per cell) and no probe chain (3.8 probes per miss at 60 % load).
+struct DenseIndex {
+  int* cells;  // nullptr: not in use
+  int x0, y0, z0;
+  unsigned nx, ny, nz;
+};
+__device__ __forceinline__ int dense_offset(const DenseIndex& d, int x, int y, int z) {
+  const unsigned ux = (unsigned)(x - d.x0), uy = (unsigned)(y - d.y0), uz = (unsigned)(z - d.z0);
+  return (ux < d.nx && uy < d.ny && uz < d.nz) ? (int)((ux * d.ny + uy) * d.nz + uz) : -1;
 }
 
 __global__ void k_fill_i32(int* __restrict__ p, int v, size_t n) {
@@ -167,50 +192,63 @@ __global__ void k_table_lookup_points(const int4* __restrict__ coords, int n, co
 }
 
 // voxel id = rank of the slot among occupied slots; buckets = {coord, id} or {0,0,0,-1} (voxel_coord_select_kernel :61-73).
-// Single block, chunked inclusive scan with carry.
+// One block per 1024 buckets: block scan, then a decoupled look-back over the totals the preceding blocks publish in
+// chunk_state (epoch << 32 | total; the epoch changes every launch, so the array never needs clearing).  A block only ever
+// waits for blocks with a smaller index, which the hardware scheduled before it.
 __global__ void __launch_bounds__(1024) k_table_assign_ids(const int4* __restrict__ coords, const int* __restrict__ slots, int num_buckets, int4* __restrict__ buckets,
-                                                          int* __restrict__ num_voxels) {
+                                                          int* __restrict__ num_voxels, const DenseIndex dense, unsigned long long* chunk_state, unsigned epoch) {
   __shared__ int warp_sums[32];
-  __shared__ int carry;
+  __shared__ int s_base;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry = 0;
+  const int b = blockIdx.x * 1024 + tid;
+  const int r = b < num_buckets ? slots[b] : -1;
+  const int flag = r >= 0 ? 1 : 0;
+  int v = flag;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) warp_sums[wid] = v;
   __syncthreads();
-  for (int base = 0; base < num_buckets; base += 1024) {
-    int b = base + tid;
-    int r = b < num_buckets ? slots[b] : -1;
-    int flag = r >= 0 ? 1 : 0;
-    int v = flag;
+  if (wid == 0) {
+    int w = warp_sums[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += t;
+      int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
     }
-    if (lane == 31) warp_sums[wid] = v;
-    __syncthreads();
-    if (wid == 0) {
-      int w = warp_sums[lane];
+    warp_sums[lane] = w;
+    const int total = __shfl_sync(0xffffffffu, w, 31);
+    volatile unsigned long long* state = chunk_state;
+    if (lane == 0) {
+      state[blockIdx.x] = ((unsigned long long)epoch << 32) | (unsigned)total;
+      __threadfence();
+    }
+    int base = 0;  // lanes split the predecessors
+    for (int p = (int)blockIdx.x - 1 - lane; p >= 0; p -= 32) {
+      unsigned long long sv;
+      while ((unsigned)((sv = state[p]) >> 32) != epoch) {}
+      base += (int)(unsigned)(sv & 0xffffffffULL);
+    }
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += t;
-      }
-      warp_sums[lane] = w;
+    for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+    if (lane == 0) {
+      s_base = base;
+      if (blockIdx.x == gridDim.x - 1) *num_voxels = base + total;
     }
-    __syncthreads();
-    int prefix = carry + (wid > 0 ? warp_sums[wid - 1] : 0) + v - flag;  // exclusive
-    if (b < num_buckets) {
-      if (flag) {
-        int4 c = coords[r];
-        buckets[b] = make_int4(c.x, c.y, c.z, prefix);
-      } else {
-        buckets[b] = make_int4(0, 0, 0, -1);
-      }
-    }
-    __syncthreads();
-    if (tid == 1023) carry = prefix + flag;
-    __syncthreads();
   }
-  if (tid == 0) *num_voxels = carry;
+  __syncthreads();
+  const int prefix = s_base + (wid > 0 ? warp_sums[wid - 1] : 0) + v - flag;  // exclusive
+  if (b < num_buckets) {
+    if (flag) {
+      int4 c = coords[r];
+      buckets[b] = make_int4(c.x, c.y, c.z, prefix);
+      if (dense.cells) dense.cells[dense_offset(dense, c.x, c.y, c.z)] = prefix;  // (inside the box by construction)
+    } else {
+      buckets[b] = make_int4(0, 0, 0, -1);
+    }
+  }
 }
 
 // accumulate_points_kernel :76-120 with double accumulators (the reference uses float atomicAdd in arrival order;
@@ -305,6 +343,7 @@ struct LinArgs {
   unsigned mask;
   int max_scan;
   const VoxelRec* vox;
+  DenseIndex dense;     // direct-mapped index over the map's bounding box (cells == nullptr: probe the hash table)
   const int4* offsets;  // generic mode
   int n_off;
   float res;
@@ -388,36 +427,116 @@ __device__ __forceinline__ int3 fixed_offset(int o) {
   return make_int3(0, 0, 0);
 }
 
+// J = [skew(pe) | -I] applied to one correspondence's  wM (symmetric-packed), wMe and w e^T M e, added to the lane's 28 running sums:
+//   B = S*wM (3x3), A = -B*S, with S = skew(pe);  H = [[A, B],[B^T, wM]],  b = [-(pe x wMe); -wMe]
+template <bool WANT_H>
+__device__ __forceinline__ void apply_jacobian(float3 pe, const PointAcc<WANT_H>& acc, float* sum) {
+  sum[0] += acc.err;
+  if (WANT_H) {
+    const float* M = acc.m;  // xx xy xz yy yz zz
+    float Mf[9] = {M[0], M[1], M[2], M[1], M[3], M[4], M[2], M[4], M[5]};
+    float B[9];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      B[0 * 3 + j] = pe.y * Mf[2 * 3 + j] - pe.z * Mf[1 * 3 + j];
+      B[1 * 3 + j] = pe.z * Mf[0 * 3 + j] - pe.x * Mf[2 * 3 + j];
+      B[2 * 3 + j] = pe.x * Mf[1 * 3 + j] - pe.y * Mf[0 * 3 + j];
+    }
+    // (B*S)[i][0] = B[i][1]*pz - B[i][2]*py ; [i][1] = -B[i][0]*pz + B[i][2]*px ; [i][2] = B[i][0]*py - B[i][1]*px
+    sum[1] += -(B[1] * pe.z - B[2] * pe.y);
+    sum[2] += -(-B[0] * pe.z + B[2] * pe.x);
+    sum[3] += -(B[0] * pe.y - B[1] * pe.x);
+    sum[4] += -(-B[3] * pe.z + B[5] * pe.x);
+    sum[5] += -(B[3] * pe.y - B[4] * pe.x);
+    sum[6] += -(B[6] * pe.y - B[7] * pe.x);
+#pragma unroll
+    for (int j = 0; j < 9; j++) sum[7 + j] += B[j];
+#pragma unroll
+    for (int j = 0; j < 6; j++) sum[16 + j] += M[j];
+    sum[22] += -(pe.y * acc.v[2] - pe.z * acc.v[1]);
+    sum[23] += -(pe.z * acc.v[0] - pe.x * acc.v[2]);
+    sum[24] += -(pe.x * acc.v[1] - pe.y * acc.v[0]);
+    sum[25] += -acc.v[0]; sum[26] += -acc.v[1]; sum[27] += -acc.v[2];
+  }
+}
+
+// per-warp staging for the compacted evaluation (below)
+constexpr int kLinQueue = 256;  // ring of pending (slot, voxel) hits: a pass adds at most 4*32, a batch of 32 is drained whenever one is full
+struct LinWarpStage {
+  float pe[3][32];    // evaluation-pose point of the warp's current points (slot-major inside each component: conflict-free)
+  float rcr[6][32];   // R C_A R^T, symmetric-packed
+  int queue[kLinQueue];
+};
+
+// one correspondence from the queue: entry = slot << 27 | voxel id
+template <bool WANT_H>
+__device__ __forceinline__ void lin_process_hit(const LinArgs& a, const LinWarpStage& st, int entry, float* sum) {
+  const int slot = (int)((unsigned)entry >> 27), id = entry & 0x7ffffff;
+  const float4* vr = reinterpret_cast<const float4*>(a.vox + id);
+  const float4 mn = __ldg(vr), c0 = __ldg(vr + 1), c1 = __ldg(vr + 2);
+  const float3 pe = make_float3(st.pe[0][slot], st.pe[1][slot], st.pe[2][slot]);
+  float rcr[6];
+#pragma unroll
+  for (int q = 0; q < 6; q++) rcr[q] = st.rcr[q][slot];
+  PointAcc<WANT_H> acc;
+#pragma unroll
+  for (int q = 0; q < 6; q++) acc.m[q] = 0.f;
+  acc.v[0] = acc.v[1] = acc.v[2] = 0.f;
+  acc.err = 0.f;
+  accumulate_voxel<WANT_H>(mn, c0, c1, true, rcr, pe, acc, a.ndt, a.res);
+  apply_jacobian<WANT_H>(pe, acc, sum);
+}
+
 // MODE: 0 = offsets from memory (DIRECT_RADIUS or anything), 1 / 7 / 27 = the reference's fixed tables.
-// G lanes share one source point and split its neighbour cells (lane s takes offsets s, s+G, ...): at 17k points a
-// one-thread-per-point mapping leaves one warp per scheduler and 27 serial dependent probes per thread; with G = 8 the
-// probes of a lane (<= 4) are issued together and the grid has 8x the warps to hide the L2 latency.
-// per-thread accumulation of the NV sums over this thread's (point, lane) tasks
-template <int MODE, bool WANT_H, int G>
-__device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl, const Pose& Te, float* sum) {
+// Two phases per warp and set of 32/G source points, so that both run at full lane efficiency:
+//  (1) lookup: G lanes share one point and split its neighbour cells (lane s takes offsets s, s+G, ...), the bucket probes
+//      of a lane (<= 4 per pass) are in flight together; only ~28 % of the probed cells hold a voxel, so nothing but the
+//      lookup itself happens here -- every hit is appended (ballot + prefix) to a per-warp queue in shared memory;
+//  (2) accumulate: whenever 32 hits are queued each lane takes ONE (point, voxel) correspondence: voxel record loads, the
+//      3x3 inversion and the Jacobian products run with all lanes busy instead of ~9 of 32.
+// The per-point terms (evaluation-pose point, R C_A R^T) are computed once per point and staged in shared memory.
+// The running sums are per lane over whatever correspondences the lane drew: the total is a sum over all of them anyway,
+// and the assignment depends only on the data, so the result is reproducible run to run.
+__device__ __forceinline__ LinWarpStage& lin_stage() {
+  __shared__ LinWarpStage stage[kLinThreads / 32];
+  return stage[threadIdx.x >> 5];
+}
+
+template <int MODE, bool WANT_H, int G, bool DENSE>
+__device__ __forceinline__ void lin_accumulate_impl(const LinArgs& a, const Pose& Tl, const Pose& Te, float* sum) {
   constexpr int NV = WANT_H ? kLinValues : 1;
   constexpr int NOFF = MODE == 0 ? 0 : MODE;
-  constexpr bool COLUMNS = (MODE == 27 && G == 1);  // one thread walks all 27 cells: 9 passes of one z-column, hash prefixes shared
+  // MODE 27: a lane walks whole z-columns (3 cells sharing the x,y hash prefix) of a contiguous run of 27/G cells, G in {1, 3, 9}
+  constexpr bool COLUMNS = (MODE == 27);
+  static_assert(MODE != 27 || G == 1 || G == 3 || G == 9, "DIRECT27 splits its 9 z-columns over 1, 3 or 9 lanes");
   constexpr int CELLS = COLUMNS ? 3 : (MODE == 0 ? 4 : ((NOFF + G - 1) / G < 4 ? (NOFF + G - 1) / G : 4));  // cells per lane per pass (loads in flight)
+  constexpr int TPW = (32 / G) * G;  // (point, lane) tasks per warp: whole points only (30 of 32 lanes at G = 3, 27 at G = 9)
+  LinWarpStage& st = lin_stage();
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
   for (int i = 0; i < NV; i++) sum[i] = 0.f;
   const int n_off = MODE == 0 ? a.n_off : NOFF;
+  const int n_pass = COLUMNS ? 9 / G : (n_off + G * CELLS - 1) / (G * CELLS);
   const long long n_tasks = (long long)a.n * G;
+  constexpr int kWarps = kLinThreads / 32;
   // warp-uniform trip count (the body uses warp votes): lanes past the end are clamped onto the last task and masked out
-  for (long long base = (long long)blockIdx.x * kLinThreads + (threadIdx.x & ~31); base < n_tasks; base += (long long)gridDim.x * kLinThreads) {
-    const long long task_raw = base + (threadIdx.x & 31);
-    const bool active = task_raw < n_tasks;
+  for (long long base = ((long long)blockIdx.x * kWarps + (threadIdx.x >> 5)) * TPW; base < n_tasks; base += (long long)gridDim.x * kWarps * TPW) {
+    const long long task_raw = base + lane;
+    const bool active = lane < TPW && task_raw < n_tasks;
     const long long task = active ? task_raw : n_tasks - 1;
     const int i = (int)(task / G);
     const int sub = (int)(task % G);
-    float4 p = a.pts[i];
-    float4 ca = a.covA[i];
-    float2 cb = a.covB[i];
-    float3 pl = transform_point(Tl, p.x, p.y, p.z);
-    float3 pe = transform_point(Te, p.x, p.y, p.z);
-    // RCR = R_lin C_A R_lin^T  (compute_derivatives.cu:75), symmetric-packed
-    float rcr[6];
-    {
+    const int slot = (lane / G) & 31;
+    const float4 p = a.pts[i];
+    const float3 pl = transform_point(Tl, p.x, p.y, p.z);
+    __syncwarp();  // the previous set's hits are all consumed before its staging is overwritten
+    if (sub == 0) {
+      const float4 ca = a.covA[i];
+      const float2 cb = a.covB[i];
+      const float3 pe = transform_point(Te, p.x, p.y, p.z);
+      st.pe[0][slot] = pe.x; st.pe[1][slot] = pe.y; st.pe[2][slot] = pe.z;
+      // RCR = R_lin C_A R_lin^T  (compute_derivatives.cu:75), symmetric-packed
       const float* R = Tl.r;
       float t[9];  // T = R*C
 #pragma unroll
@@ -426,41 +545,29 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl,
         t[r * 3 + 1] = (R[r * 3] * ca.y + R[r * 3 + 1] * ca.w) + R[r * 3 + 2] * cb.x;
         t[r * 3 + 2] = (R[r * 3] * ca.z + R[r * 3 + 1] * cb.x) + R[r * 3 + 2] * cb.y;
       }
-      rcr[0] = (t[0] * R[0] + t[1] * R[1]) + t[2] * R[2];
-      rcr[1] = (t[0] * R[3] + t[1] * R[4]) + t[2] * R[5];
-      rcr[2] = (t[0] * R[6] + t[1] * R[7]) + t[2] * R[8];
-      rcr[3] = (t[3] * R[3] + t[4] * R[4]) + t[5] * R[5];
-      rcr[4] = (t[3] * R[6] + t[4] * R[7]) + t[5] * R[8];
-      rcr[5] = (t[6] * R[6] + t[7] * R[7]) + t[8] * R[8];
+      st.rcr[0][slot] = (t[0] * R[0] + t[1] * R[1]) + t[2] * R[2];
+      st.rcr[1][slot] = (t[0] * R[3] + t[1] * R[4]) + t[2] * R[5];
+      st.rcr[2][slot] = (t[0] * R[6] + t[1] * R[7]) + t[2] * R[8];
+      st.rcr[3][slot] = (t[3] * R[3] + t[4] * R[4]) + t[5] * R[5];
+      st.rcr[4][slot] = (t[3] * R[6] + t[4] * R[7]) + t[5] * R[8];
+      st.rcr[5][slot] = (t[6] * R[6] + t[7] * R[7]) + t[8] * R[8];
     }
     const int bx = voxel_coord1(pl.x, a.res), by = voxel_coord1(pl.y, a.res), bz = voxel_coord1(pl.z, a.res);
-    PointAcc<WANT_H> acc;
-#pragma unroll
-    for (int q = 0; q < 6; q++) acc.m[q] = 0.f;
-    acc.v[0] = acc.v[1] = acc.v[2] = 0.f;
-    acc.err = 0.f;
+    unsigned head = 0, tail = 0;  // warp-uniform ring indices
 
     // the 27 neighbours share hash prefixes (vector3i_hash folds x, then y, then z): 9 + 9 + 27 folds instead of 81
     uint64_t kzm[3] = {0, 0, 0};
-    if (COLUMNS) {
+    if (COLUMNS && !DENSE) {
 #pragma unroll
       for (int d = 0; d < 3; d++) kzm[d] = hash_mix((uint64_t)(int64_t)(bz + d - 1));
     }
-    for (int o_base = 0; o_base < n_off; o_base += G * CELLS) {  // same trip count in every lane (warp votes below)
-      const int o0 = o_base + sub;
-      // phase 1: all first-probe bucket loads of this lane in flight together
-      int cx[CELLS], cy[CELLS], cz[CELLS];
-      unsigned pos[CELLS];
-      int4 bk[CELLS];
+    for (int pass = 0; pass < n_pass; pass++) {  // same trip count in every lane (warp votes below)
+      const int o0 = COLUMNS ? sub * (27 / G) + pass * 3 : pass * (G * CELLS) + sub;
+      int cx[CELLS], cy[CELLS], cz[CELLS], found[CELLS];
       bool valid[CELLS];
-      uint64_t hxy = 0;
-      if (COLUMNS) {  // o0 = 9*ix + 3*iy (i-major order of fast_vgicp_cuda.cu:68-74), cells o0, o0+1, o0+2 = iz 0..2
-        const int ix = o0 / 9, iy = (o0 / 3) % 3;
-        hxy = hash_fold(hash_fold(0, hash_mix((uint64_t)(int64_t)(bx + ix - 1))), hash_mix((uint64_t)(int64_t)(by + iy - 1)));
-      }
 #pragma unroll
       for (int j = 0; j < CELLS; j++) {
-        const int o = o0 + j * G;
+        const int o = COLUMNS ? o0 + j : o0 + j * G;
         valid[j] = active && o < n_off;
         int3 off;
         if (MODE == 0) {
@@ -470,73 +577,65 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl,
           off = fixed_offset<MODE>(valid[j] ? o : 0);
         }
         cx[j] = bx + off.x; cy[j] = by + off.y; cz[j] = bz + off.z;
-        const uint64_t hsh = COLUMNS ? hash_fold(hxy, kzm[j]) : vector3i_hash(cx[j], cy[j], cz[j]);
-        pos[j] = (unsigned)(hsh & a.mask);
-        bk[j] = __ldg(&a.buckets[pos[j]]);
       }
-      // phase 2: resolve (further probes are rare: the table is <= ~50% full), then unconditional voxel loads
-      int id[CELLS];
-      float4 mn[CELLS], c0[CELLS], c1[CELLS];
+      if (DENSE) {  // one 4-byte load per cell (the three cells of a z-column are adjacent)
+#pragma unroll
+        for (int j = 0; j < CELLS; j++) {
+          const int off = dense_offset(a.dense, cx[j], cy[j], cz[j]);
+          found[j] = (valid[j] && off >= 0) ? __ldg(&a.dense.cells[off]) : -1;
+        }
+      } else {
+        // all first-probe bucket loads of this lane in flight together
+        unsigned pos[CELLS];
+        int4 bk[CELLS];
+        uint64_t hxy = 0;
+        if (COLUMNS) {  // o0 = 9*ix + 3*iy (i-major order of fast_vgicp_cuda.cu:68-74), cells o0, o0+1, o0+2 = iz 0..2
+          const int ix = o0 / 9, iy = (o0 / 3) % 3;
+          hxy = hash_fold(hash_fold(0, hash_mix((uint64_t)(int64_t)(bx + ix - 1))), hash_mix((uint64_t)(int64_t)(by + iy - 1)));
+        }
+#pragma unroll
+        for (int j = 0; j < CELLS; j++) {
+          const uint64_t hsh = COLUMNS ? hash_fold(hxy, kzm[j]) : vector3i_hash(cx[j], cy[j], cz[j]);
+          pos[j] = (unsigned)(hsh & a.mask);
+          bk[j] = __ldg(&a.buckets[pos[j]]);
+        }
+        // resolve (find_voxel_correspondences.cu:39-51)
+#pragma unroll
+        for (int j = 0; j < CELLS; j++) {
+          int4 b = bk[j];
+          found[j] = -1;
+          for (int s = 0; s < a.max_scan; s++) {
+            if (b.w < 0) break;
+            if (b.x == cx[j] && b.y == cy[j] && b.z == cz[j]) { found[j] = b.w; break; }
+            pos[j] = (pos[j] + 1) & a.mask;
+            if (s + 1 < a.max_scan) b = __ldg(&a.buckets[pos[j]]);
+          }
+        }
+      }
+      // queue the hits
 #pragma unroll
       for (int j = 0; j < CELLS; j++) {
-        int4 b = bk[j];
-        int found = -1;
-        for (int s = 0; s < a.max_scan; s++) {  // find_voxel_correspondences.cu:39-51
-          if (b.w < 0) break;
-          if (b.x == cx[j] && b.y == cy[j] && b.z == cz[j]) { found = b.w; break; }
-          pos[j] = (pos[j] + 1) & a.mask;
-          if (s + 1 < a.max_scan) b = __ldg(&a.buckets[pos[j]]);
-        }
-        id[j] = valid[j] ? found : -1;
-        // voxel record: three 16-byte loads, predicated per lane (a miss needs no data), all issued before any of the math below
-        mn[j] = c0[j] = c1[j] = make_float4(0.f, 0.f, 0.f, 1.f);
-        if (id[j] >= 0) {
-          const float4* vr = reinterpret_cast<const float4*>(a.vox + id[j]);
-          mn[j] = __ldg(vr); c0[j] = __ldg(vr + 1); c1[j] = __ldg(vr + 2);
-        }
+        const bool hit = valid[j] && found[j] >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) st.queue[(tail + __popc(m & lt_mask)) & (kLinQueue - 1)] = (slot << 27) | found[j];
+        tail += __popc(m);
       }
-#pragma unroll
-      for (int j = 0; j < CELLS; j++) {
-        // neighbouring points see the same empty cells (above/below a surface): when no lane of the warp hit this cell, the
-        // 3x3 inversion and the accumulation are skipped for the whole warp
-        if (__any_sync(0xffffffffu, id[j] >= 0)) accumulate_voxel<WANT_H>(mn[j], c0[j], c1[j], id[j] >= 0, rcr, pe, acc, a.ndt, a.res);
+      __syncwarp();
+      while (tail - head >= 32u) {  // full batches: one correspondence per lane
+        lin_process_hit<WANT_H>(a, st, st.queue[(head + lane) & (kLinQueue - 1)], sum);
+        head += 32u;
       }
     }
-
-    if (WANT_H) {
-      // B = S*Msum (3x3), A = -B*S, with S = skew(pe);  H = [[A, B],[B^T, Msum]],  b = [-(pe x v); -v]
-      // (linear in Msum and v, so every lane applies J to its own partial sums)
-      const float* M = acc.m;  // xx xy xz yy yz zz
-      float Mf[9] = {M[0], M[1], M[2], M[1], M[3], M[4], M[2], M[4], M[5]};
-      float B[9];
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        B[0 * 3 + j] = pe.y * Mf[2 * 3 + j] - pe.z * Mf[1 * 3 + j];
-        B[1 * 3 + j] = pe.z * Mf[0 * 3 + j] - pe.x * Mf[2 * 3 + j];
-        B[2 * 3 + j] = pe.x * Mf[1 * 3 + j] - pe.y * Mf[0 * 3 + j];
-      }
-      // (B*S)[i][0] = B[i][1]*pz - B[i][2]*py ; [i][1] = -B[i][0]*pz + B[i][2]*px ; [i][2] = B[i][0]*py - B[i][1]*px
-      float A00 = -(B[1] * pe.z - B[2] * pe.y);
-      float A01 = -(-B[0] * pe.z + B[2] * pe.x);
-      float A02 = -(B[0] * pe.y - B[1] * pe.x);
-      float A11 = -(-B[3] * pe.z + B[5] * pe.x);
-      float A12 = -(B[3] * pe.y - B[4] * pe.x);
-      float A22 = -(B[6] * pe.y - B[7] * pe.x);
-      sum[0] += acc.err;
-      sum[1] += A00; sum[2] += A01; sum[3] += A02; sum[4] += A11; sum[5] += A12; sum[6] += A22;
-#pragma unroll
-      for (int j = 0; j < 9; j++) sum[7 + j] += B[j];
-#pragma unroll
-      for (int j = 0; j < 6; j++) sum[16 + j] += M[j];
-      sum[22] += -(pe.y * acc.v[2] - pe.z * acc.v[1]);
-      sum[23] += -(pe.z * acc.v[0] - pe.x * acc.v[2]);
-      sum[24] += -(pe.x * acc.v[1] - pe.y * acc.v[0]);
-      sum[25] += -acc.v[0]; sum[26] += -acc.v[1]; sum[27] += -acc.v[2];
-    } else {
-      sum[0] += acc.err;
+    if (tail != head) {  // the set's last, partial batch
+      if (lane < (int)(tail - head)) lin_process_hit<WANT_H>(a, st, st.queue[(head + lane) & (kLinQueue - 1)], sum);
     }
   }
+}
 
+template <int MODE, bool WANT_H, int G>
+__device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl, const Pose& Te, float* sum) {
+  if (a.dense.cells) lin_accumulate_impl<MODE, WANT_H, G, true>(a, Tl, Te, sum);  // (grid-uniform branch)
+  else lin_accumulate_impl<MODE, WANT_H, G, false>(a, Tl, Te, sum);
 }
 
 // block reduction (warp shuffles in float -> shared in double -> per-block partial), ticket, fixed-order fold by the last

@@ -192,6 +192,13 @@ VGICP_API int vgicp_set_align_mode(vgicp_handle h, int mode);
 /* k-NN engine used by find_*_neighbors: 0 = multi-level hash grid (default), 1 = warp-cooperative scan of the whole cloud,
  * 2 = one-thread-per-query scan (the shape of the reference's brute_force_knn.cu).  All three return identical rows. */
 VGICP_API int vgicp_set_knn_mode(vgicp_handle h, int mode);
+/* Voxel lookup structure used by the evaluation kernels (update_correspondences + compute_derivatives fused): 0 = a direct-mapped
+ * cell -> voxel-id array over the bounding box of the target's voxel coordinates, built next to the hash table whenever that box
+ * has at most 16 Mi cells (default; any LiDAR-like cloud), 1 = always probe the reference-layout hash table
+ * (gaussian_voxelmap.cu:12-73 / find_voxel_correspondences.cu:32-60).  Both return the same voxel ids: a table lookup answers
+ * "is this coordinate a voxel of the map, and which", and the map's set of voxels (including the reference's drop rule for
+ * voxels that fall off the 10-probe window) is decided by the table build alone. */
+VGICP_API int vgicp_set_voxel_index(vgicp_handle h, int mode);
 /* per-kernel timing with CUDA events on the handle's stream (off by default; enabling resets the counters) */
 enum {
   VGICP_PROF_UNPACK = 0, VGICP_PROF_KNN = 1, VGICP_PROF_COVARIANCE = 2, VGICP_PROF_VOXELMAP = 3, VGICP_PROF_LINEARIZE = 4, VGICP_PROF_ERROR = 5,

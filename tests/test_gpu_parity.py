@@ -238,6 +238,41 @@ def test_correspondences_and_linear_system(prepared, relative_pose, method, radi
             # bitwise reproducible (fixed-order reduction)
             err2, H2, b2 = c.compute_error(Te, True)
             assert err2 == err and np.array_equal(H2, H) and np.array_equal(b2, b)
+            # the reference-layout hash table and the direct-mapped index find the same voxels in the same order
+            c.set_voxel_index(1)
+            err3, H3, b3 = c.compute_error(Te, True)
+            e3, _, _ = c.compute_error(Te, False)
+            c.set_voxel_index(0)
+            assert err3 == err and np.array_equal(H3, H) and np.array_equal(b3, b) and e3 == e1
+    c.close()
+
+
+def test_voxel_index_falls_back_to_the_hash_table(prepared, relative_pose):
+    """A target whose voxel bounding box is too large for the direct-mapped index (one far outlier) is evaluated through the
+    hash table alone; the linear system still matches the oracle and the in-box case."""
+    from fast_gicp_b200.core import Core
+
+    tgt = np.vstack([prepared["tgt"], np.array([[3.0e6, -2.0e6, 1.0e6]], dtype=np.float32)])
+    c = Core(0)
+    c.set_neighbor_search_method(O.DIRECT27)
+    c.set_target_cloud(tgt)
+    c.find_target_neighbors(20)
+    c.calculate_target_covariances(O.REG_PLANE)
+    c.create_target_voxelmap()
+    c.set_source_cloud(prepared["src"])
+    c.find_source_neighbors(20)
+    c.calculate_source_covariances(O.REG_PLANE)
+    t_cov = sym(c.get_target_covariances()).astype(np.float32)
+    vm = O.VoxelMap(tgt, t_cov, 1.0, accum_double=True)
+    offs = O.offsets(O.DIRECT27, -1)
+    s_cov = sym(prepared["s_cov"]).astype(np.float32)
+    err, H, b = c.linearize(relative_pose)
+    e0, H0, b0, _ = O.evaluate(vm, prepared["src"], s_cov, offs, relative_pose, relative_pose, True)
+    assert abs(err - e0) <= 2e-5 * abs(e0)
+    assert np.abs(H - H0).max() <= 2e-5 * np.abs(H0).max()
+    c.set_voxel_index(1)  # no change: the index was never built
+    err1, H1, b1 = c.linearize(relative_pose)
+    assert err1 == err and np.array_equal(H1, H) and np.array_equal(b1, b)
     c.close()
 
 
