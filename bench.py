@@ -275,7 +275,9 @@ def main():
     for c in cores:
         if ndt:
             c.set_problem(2)
-    hint = 1 if S > 1 else 0  # many handles share the GPU -> throughput launch shapes (vgicp_set_execution_hint)
+    # latency launch shapes + results through mapped host memory on every stream: measured faster than the throughput hint even at 16
+    # handles per GPU (7.1k vs 6.7k registrations/s) since the evaluation kernel compacts its hits (scripts/exp_concurrency.py)
+    hint = 0
     for c in cores:
         c.set_resolution(w["res"])
         c.set_neighbor_search_method(w["method"])

@@ -179,10 +179,10 @@ VGICP_API int vgicp_clear_source_shard(vgicp_handle h);
  * No kNN and no per-point covariances are involved (the reference's NDTCuda never computes them). */
 VGICP_API int vgicp_set_problem(vgicp_handle h, int problem);
 VGICP_API int vgicp_ndt_create_voxelmaps(vgicp_handle h);
-/* Launch-shape hint: 0 = latency (default; one registration should finish as soon as possible: a point's neighbour cells are
- * split over several lanes, the persistent k-NN kernel takes 4 blocks per SM), 1 = throughput (many handles share the GPU on
- * separate streams: one lane per point and 2 k-NN blocks per SM -- fewer instructions per registration, longer kernels).
- * Results are identical up to the float rounding of per-warp partial sums. */
+/* Execution hint: 0 = latency (default: the persistent k-NN kernel takes 4 blocks per SM; every evaluation writes its 43 doubles
+ * straight into mapped host memory and the calling thread spins on a completion word), 1 = throughput / polite (2 k-NN blocks per SM;
+ * evaluations are read back with a copy and a stream wait, so the host thread sleeps instead of spinning).  Results are identical.
+ * On a B200 host with cores to spare the latency shape is also the faster one with 16 handles per GPU (bench.py uses it). */
 VGICP_API int vgicp_set_execution_hint(vgicp_handle h, int hint);
 /* vgicp_align driver: 1 = host-driven loop over the evaluation kernels (default; one 344-byte readback per evaluation, like
  * the reference), 0 = device-resident loop (the LM state machine runs in the last block of each evaluation kernel, the host
