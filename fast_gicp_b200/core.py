@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "vgicp_lsq_default_params", "vgicp_align", "vgicp_transform_source",
     "vgicp_get_launch_count", "vgicp_synchronize", "vgicp_get_stream",
     "vgicp_set_source_cloud_device", "vgicp_set_target_cloud_device", "vgicp_set_profiling", "vgicp_get_profile", "vgicp_profile_category_name",
-    "vgicp_set_knn_mode", "vgicp_set_voxel_index", "vgicp_register", "vgicp_set_align_mode", "vgicp_get_fitness_score", "vgicp_set_execution_hint", "vgicp_set_problem", "vgicp_ndt_create_voxelmaps",
+    "vgicp_set_knn_mode", "vgicp_set_voxel_index", "vgicp_set_speculation", "vgicp_register", "vgicp_set_align_mode", "vgicp_get_fitness_score", "vgicp_set_execution_hint", "vgicp_set_problem", "vgicp_ndt_create_voxelmaps",
     "vgicp_comm_export", "vgicp_comm_init", "vgicp_comm_shutdown", "vgicp_comm_error", "vgicp_set_source_shard", "vgicp_clear_source_shard",
 ]
 PROF_NUM_CATEGORIES = 7
@@ -126,6 +126,7 @@ def load_library():
         "vgicp_set_profiling": [hp, C.c_int],
         "vgicp_set_knn_mode": [hp, C.c_int],
         "vgicp_set_voxel_index": [hp, C.c_int],
+        "vgicp_set_speculation": [hp, C.c_int],
         "vgicp_set_align_mode": [hp, C.c_int],
         "vgicp_get_fitness_score": [hp, dp, C.c_double, dp],
         "vgicp_set_execution_hint": [hp, C.c_int],
@@ -261,6 +262,10 @@ class Core:
     def set_voxel_index(self, mode):
         """0: direct-mapped voxel index when the map's bounding box fits (default), 1: hash table only."""
         self._check(self._lib.vgicp_set_voxel_index(self._h, int(mode)))
+
+    def set_speculation(self, enable):
+        """LM trial evaluations also linearise at the trial pose (default on); results are identical either way."""
+        self._check(self._lib.vgicp_set_speculation(self._h, int(bool(enable))))
 
     def set_profiling(self, enable):
         self._check(self._lib.vgicp_set_profiling(self._h, int(bool(enable))))

@@ -125,6 +125,7 @@ struct vgicp_context {
   int comm_rank = 0, comm_ranks = 0;
   unsigned long long comm_seq = 0;
   int shard_begin = 0, shard_end = -1;           // evaluations cover source points [begin, end)
+  int speculate = 1;  // LM trial evaluations also linearise at the trial pose (vgicp_set_speculation)
   int exec_hint = 0;  // 0 = latency (one registration should finish as soon as possible), 1 = throughput (many concurrent handles)
   int align_mode = 1;  // 1 = host-driven loop over the evaluation kernels (default: faster today), 0 = device-resident LM chain
   LmState* d_lm = nullptr;
@@ -536,7 +537,7 @@ LinLaunch make_lin_launch(vgicp_handle h) {
 }
 
 // one evaluation: launches the fused lookup+derivative kernel; result lands in h->h_out after the stream sync
-int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H, bool direct_to_host = false) {
+int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H, bool direct_to_host = false, bool spec = false) {
   LinLaunch L = make_lin_launch(h);
   LinArgs& a = L.a;
   a.Teval = Teval;
@@ -549,7 +550,8 @@ int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H, bool direct
   const int grid = L.grid, G = L.G;
 #define LAUNCH_LIN_G(MODE, GG)                                                           \
   do {                                                                                   \
-    if (want_H) k_linearize<MODE, true, GG><<<grid, kLinThreads, 0, h->stream>>>(a);     \
+    if (spec) k_linearize_spec<MODE, GG><<<grid, kLinThreads, 0, h->stream>>>(a);        \
+    else if (want_H) k_linearize<MODE, true, GG><<<grid, kLinThreads, 0, h->stream>>>(a); \
     else k_linearize<MODE, false, GG><<<grid, kLinThreads, 0, h->stream>>>(a);           \
   } while (0)
 #define LAUNCH_LIN(MODE)                 \
@@ -686,6 +688,36 @@ int evaluate(vgicp_handle h, const double* T, double* H36, double* b6, double* e
   return VGICP_OK;
 }
 
+// trial-pose evaluation for the LM loop: error at T over the current correspondences (*err_old) plus the linearisation at T itself
+// (k_linearize_spec); h->lin stays the current linearisation point
+int evaluate_spec(vgicp_handle h, const double* T, double* err_old, double* H36, double* b6, double* err_new) {
+  const bool direct = h->exec_hint == 0;
+  int rc = launch_linearize(h, to_pose(T), true, direct, true);
+  if (rc) return rc;
+  if (direct) {
+    const unsigned long long want = h->eval_seq;
+    volatile unsigned long long* flag = h->h_flag;
+    long spins = 0;
+    while (*flag != want) {
+      __builtin_ia32_pause();
+      if (++spins > 2000000L) {
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        if (*flag != want) return fail(h, VGICP_ERR_CUDA, "evaluate: kernel finished without publishing its result");
+        break;
+      }
+    }
+    __sync_synchronize();
+  } else {
+    CU_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * 44, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  *err_new = h->h_out[0];
+  memcpy(H36, h->h_out + 1, 36 * sizeof(double));
+  memcpy(b6, h->h_out + 37, 6 * sizeof(double));
+  *err_old = h->h_out[43];
+  return VGICP_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================================
@@ -731,7 +763,7 @@ int vgicp_create(int device, vgicp_handle* out) {
   if (ok) *h->h_flag = 0;
   ok = ok && cudaMalloc(&h->d_lm, sizeof(LmState)) == cudaSuccess;
   ok = ok && cudaMallocHost(&h->h_lm, sizeof(LmState)) == cudaSuccess;
-  ok = ok && h->partials.reserve((size_t)kLinMaxBlocks * kLinValues) == cudaSuccess;
+  ok = ok && h->partials.reserve((size_t)kLinMaxBlocks * kLinStride) == cudaSuccess;
   ok = ok && cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
   if (!ok) {
@@ -1168,12 +1200,22 @@ int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* 
   bool converged = false;
   memset(res, 0, sizeof(*res));
   for (int i = 0; i < 6; i++) res->H[i * 7] = 1.0;  // final_hessian_.setIdentity()
+  // speculative evaluation: every LM trial also linearises at the trial pose, so an accepted step needs no launch of its own
+  const bool speculate = h->speculate != 0 && !P.use_gauss_newton;
+  bool have_next = false;
+  double Hn[36], bn[6], yn = 0.0;
   for (int it = 0; it < P.max_iterations && !converged; it++) {
     res->nr_iterations = it;
     double H[36], b[6], nb[6], d[6], y0 = 0.0;
     h->lin = to_pose(x0.m);
     h->has_lin = true;
-    int rc = evaluate(h, x0.m, H, b, &y0);
+    int rc = VGICP_OK;
+    if (have_next) {  // linearised at this very pose by the trial evaluation that accepted it
+      memcpy(H, Hn, sizeof(H)); memcpy(b, bn, sizeof(b)); y0 = yn;
+      have_next = false;
+    } else {
+      rc = evaluate(h, x0.m, H, b, &y0);
+    }
     if (rc) return rc;
     res->n_linearize++;
     for (int j = 0; j < 6; j++) nb[j] = -b[j];
@@ -1200,7 +1242,7 @@ int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* 
         delta = se3_exp(d);
         Iso3d xi = iso_mul(delta, x0);
         double yi = 0.0;
-        rc = evaluate(h, xi.m, nullptr, nullptr, &yi);
+        rc = speculate ? evaluate_spec(h, xi.m, &yi, Hn, bn, &yn) : evaluate(h, xi.m, nullptr, nullptr, &yi);
         if (rc) return rc;
         res->n_compute_error++;
         double den = 0.0;
@@ -1213,6 +1255,7 @@ int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* 
           continue;
         }
         x0 = xi;
+        have_next = speculate;
         double f = 1.0 - pow(2.0 * rho - 1.0, 3);
         lambda = lambda * fmax(1.0 / 3.0, f);
         memcpy(res->H, H, sizeof(H));
@@ -1395,6 +1438,12 @@ int vgicp_set_knn_mode(vgicp_handle h, int mode) {
   CHECK_HANDLE(h);
   if (mode < 0 || mode > 2) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_knn_mode: 0 grid, 1 warp scan, 2 legacy scan");
   h->knn_mode = mode;
+  return VGICP_OK;
+}
+
+int vgicp_set_speculation(vgicp_handle h, int enable) {
+  CHECK_HANDLE(h);
+  h->speculate = enable ? 1 : 0;
   return VGICP_OK;
 }
 

@@ -28,6 +28,7 @@ namespace vgicp {
 constexpr int kLinThreads = 128;     // block size of the linearize kernel
 constexpr int kLinMaxBlocks = 592;   // 4 x 148 SMs: upper bound on partial sums the last block has to fold (more resident warps only thrash L1: measured)
 constexpr int kLinValues = 28;       // 21 unique H + 6 b + 1 err
+constexpr int kLinStride = 32;       // row length of the partial-sum arrays (the speculative evaluation carries 29 values)
 
 struct Pose {      // float image of an Eigen::Isometry3f: R row-major here, t
   float r[9];
@@ -349,7 +350,7 @@ struct LinArgs {
   float res;
   int ndt;  // 0: VGICP weights (sqrt(n), compute_derivatives.cu:78); 1: NDT (Cauchy weight, voxels with <= 6 points skipped, ndt_compute_derivatives.cu)
   Pose Tlin, Teval;
-  double* partials;       // [gridDim.x][kLinValues]
+  double* partials;       // [gridDim.x][kLinStride]
   unsigned int* ticket;   // zero before first launch; reset by the last block
   double* out;            // [43]: err, H (36, column-major), b (6); may be mapped pinned host memory
   volatile unsigned long long* done_flag;  // optional (mapped host memory): set to done_seq once `out` is complete
@@ -641,9 +642,9 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl,
 // block reduction (warp shuffles in float -> shared in double -> per-block partial), ticket, fixed-order fold by the last
 // block.  Returns true in every thread of the last block; the folded sums are then in fin[0][0..NV).
 template <int NV>
-__device__ __forceinline__ bool lin_reduce(const LinArgs& a, const float* sum, double (*fin)[kLinValues]) {
+__device__ __forceinline__ bool lin_reduce(const LinArgs& a, const float* sum, double (*fin)[kLinStride]) {
   // ---- block reduction: warp shuffles (float) -> shared (double) -> per-block partial ----
-  __shared__ double sh[kLinThreads / 32][kLinValues];
+  __shared__ double sh[kLinThreads / 32][kLinStride];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -658,7 +659,7 @@ __device__ __forceinline__ bool lin_reduce(const LinArgs& a, const float* sum, d
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < kLinThreads / 32; w++) s += sh[w][threadIdx.x];
-    a.partials[(size_t)blockIdx.x * kLinValues + threadIdx.x] = s;
+    a.partials[(size_t)blockIdx.x * kLinStride + threadIdx.x] = s;
   }
   __threadfence();
   __syncthreads();
@@ -681,11 +682,11 @@ __device__ __forceinline__ bool lin_reduce(const LinArgs& a, const float* sum, d
       for (; b + 4 * 15 < gridDim.x; b += 4 * 16) {
         double t[16];
 #pragma unroll
-        for (int u = 0; u < 16; u++) t[u] = __ldcg(part + (size_t)(b + 4 * u) * kLinValues);
+        for (int u = 0; u < 16; u++) t[u] = __ldcg(part + (size_t)(b + 4 * u) * kLinStride);
 #pragma unroll
         for (int u = 0; u < 16; u++) s += t[u];
       }
-      for (; b < gridDim.x; b += 4) s += __ldcg(part + (size_t)b * kLinValues);
+      for (; b < gridDim.x; b += 4) s += __ldcg(part + (size_t)b * kLinStride);
       fin[chain][v] = s;
     }
   }
@@ -758,7 +759,7 @@ __device__ __forceinline__ void lin_unpack(const double* s, double* out) {
 template <int MODE, bool WANT_H, int G>
 __global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
   constexpr int NV = WANT_H ? kLinValues : 1;
-  __shared__ double fin[4][kLinValues];
+  __shared__ double fin[4][kLinStride];
   float sum[NV];
   lin_accumulate<MODE, WANT_H, G>(a, a.Tlin, a.Teval, sum);
   if (!lin_reduce<NV>(a, sum, fin)) return;
@@ -766,6 +767,40 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
     lin_unpack<WANT_H>(fin[0], a.out);
     *a.ticket = 0u;
     if (a.done_flag) {  // the host spins on this word instead of waiting for the stream (saves the copy + wake-up latency)
+      __threadfence_system();
+      *a.done_flag = a.done_seq;
+    }
+  }
+}
+
+// Speculative LM evaluation (lsq_registration_impl.hpp:141-160): one launch returns what the optimiser needs to judge a trial
+// pose xi = a.Teval -- the error at xi over the correspondences of the current linearisation point a.Tlin (compute_error) -- and
+// what it needs next if the step is accepted: the full linearisation AT xi (update_correspondences + compute_error(H, b) with
+// Tlin = Teval = xi).  Both are the sums the two separate launches would produce, bit for bit (same grid, same per-lane order);
+// an accepted step saves a launch and a host round trip, a rejected one discards the second half.
+//   out[0..42] = err, H, b at xi (linearised at xi);  out[43] = err at xi over the old correspondences
+template <int MODE, int G>
+__global__ void __launch_bounds__(kLinThreads) k_linearize_spec(const LinArgs a) {
+  constexpr int NV = kLinValues + 1;
+  __shared__ double fin[4][kLinStride];
+  float sum[NV];
+  {
+    float e_old[1];
+    lin_accumulate<MODE, false, G>(a, a.Tlin, a.Teval, e_old);
+    sum[kLinValues] = e_old[0];
+  }
+  {
+    float lin[kLinValues];
+    lin_accumulate<MODE, true, G>(a, a.Teval, a.Teval, lin);
+#pragma unroll
+    for (int i = 0; i < kLinValues; i++) sum[i] = lin[i];
+  }
+  if (!lin_reduce<NV>(a, sum, fin)) return;
+  if (threadIdx.x == 0) {
+    lin_unpack<true>(fin[0], a.out);
+    a.out[43] = fin[0][kLinValues];
+    *a.ticket = 0u;
+    if (a.done_flag) {
       __threadfence_system();
       *a.done_flag = a.done_seq;
     }
@@ -887,7 +922,7 @@ __device__ void lm_advance(LmState* st, const double* out /*err, H, b*/) {
 
 template <int MODE, int G>
 __global__ void __launch_bounds__(kLinThreads) k_lm_step(const LinArgs a, LmState* st) {
-  __shared__ double fin[4][kLinValues];
+  __shared__ double fin[4][kLinStride];
   __shared__ double out[44];
   const int phase = st->phase;
   if (phase == kLmDone) return;

@@ -199,6 +199,12 @@ VGICP_API int vgicp_set_knn_mode(vgicp_handle h, int mode);
  * "is this coordinate a voxel of the map, and which", and the map's set of voxels (including the reference's drop rule for
  * voxels that fall off the 10-probe window) is decided by the table build alone. */
 VGICP_API int vgicp_set_voxel_index(vgicp_handle h, int mode);
+/* vgicp_align, Levenberg-Marquardt: 1 (default) = each trial evaluation (compute_error at x0*delta, lsq_registration_impl.hpp:141)
+ * also linearises at the trial pose in the same launch, so that the next iteration of an accepted step
+ * (update_correspondences + compute_error(H, b), fast_vgicp_cuda_impl.hpp:170-173) is already there: ~6 instead of ~9 launches
+ * and host round trips per registration; a rejected trial discards it.  0 = one launch per evaluation, as the reference.
+ * The iterates, the result and the n_linearize / n_compute_error counters are identical either way. */
+VGICP_API int vgicp_set_speculation(vgicp_handle h, int enable);
 /* per-kernel timing with CUDA events on the handle's stream (off by default; enabling resets the counters) */
 enum {
   VGICP_PROF_UNPACK = 0, VGICP_PROF_KNN = 1, VGICP_PROF_COVARIANCE = 2, VGICP_PROF_VOXELMAP = 3, VGICP_PROF_LINEARIZE = 4, VGICP_PROF_ERROR = 5,

@@ -26,11 +26,12 @@ def worker(core, n, out, i):
         r = core.align()
     out[i] = r.nr_iterations
 
-for T in (1, 2, 4, 8, 16, 32):
+for T in [int(x) for x in os.environ.get("TS", "1,2,4,8,16,32").split(",")]:
     cores = [Core(0) for _ in range(T)]
     for c in cores:
         c.set_neighbor_search_method("DIRECT27")
         c.set_execution_hint(int(os.environ.get("HINT", "0")))
+        c.set_speculation(int(os.environ.get("SPEC", "1")))
     out = [None] * T
     for c in cores: worker(c, 3, out, 0)
     torch.cuda.synchronize()

@@ -276,6 +276,32 @@ def test_voxel_index_falls_back_to_the_hash_table(prepared, relative_pose):
     c.close()
 
 
+@pytest.mark.parametrize("method,radius", [(O.DIRECT1, -1), (O.DIRECT7, -1), (O.DIRECT27, -1), (O.DIRECT_RADIUS, 1.5)])
+def test_speculative_evaluation_is_invisible(prepared, method, radius):
+    """LM with the trial evaluation fused with the next linearisation (default) walks bit-identical iterates to one launch per
+    evaluation, with the same evaluation counters and fewer launches; also from a poor guess, where trials get rejected."""
+    from fast_gicp_b200.core import Core
+
+    rng = np.random.default_rng(17)
+    guesses = [np.eye(4), random_pose(rng, 0.15, 1.5)]
+    out = {}
+    for spec in (1, 0):
+        c = Core(0)
+        c.set_speculation(spec)
+        _setup_pair(c, prepared, method, radius)
+        rows = []
+        for g in guesses:
+            n0 = c.launch_count()
+            r = c.align(guess=g)
+            rows.append((np.array(r.T).copy(), np.array(r.H).copy(), r.nr_iterations, r.n_linearize, r.n_compute_error, bool(r.converged), c.launch_count() - n0))
+        out[spec] = rows
+        c.close()
+    for a, b in zip(out[1], out[0]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert a[2:6] == b[2:6]
+        assert a[6] < b[6]  # fewer launches
+
+
 @pytest.mark.parametrize("method", [O.DIRECT1, O.DIRECT7, O.DIRECT27])
 def test_align_matches_oracle_and_ground_truth(prepared, relative_pose, method):
     """Whole registration vs the float oracle (north_star tolerance) and vs data/relative.txt (reference's gate)."""
