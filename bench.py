@@ -194,13 +194,20 @@ def main():
     sys.stdout.flush()
     _REAL_STDOUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
+    # a run that stops making progress leaves the Python stacks of all threads on stderr every 5 minutes
+    import faulthandler
+
+    faulthandler.dump_traceback_later(300, repeat=True, file=sys.stderr)
+    print("[bench] start", file=sys.stderr, flush=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--streams", type=int, default=16, help="concurrent registration streams per GPU (host thread + handle each)")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="concurrent registration streams per GPU (host thread + handle each); default 16, or 8 when more than 2 ranks share the host "
+                         "(every stream's thread spins on its completion word)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -232,7 +239,8 @@ def main():
 
     tgt, src = w["target"], w["source"]
     n_t, n_s = len(tgt), len(src)
-    K, W, S = args.steps, args.warmup, max(1, args.streams)
+    K, W = args.steps, args.warmup
+    S = args.streams if args.streams > 0 else (16 if int(os.environ.get("WORLD_SIZE", "1")) <= 2 else 8)
     _t0 = time.perf_counter()
 
     def note(msg):
@@ -301,14 +309,9 @@ def main():
             c.set_cloud_device("source", sp + pi * n_s * 12, n_s, 12)
             c.ndt_create_voxelmaps()
             return c.align()
-        c.set_cloud_device("target", tp + pi * n_t * 12, n_t, 12)
-        c.find_target_neighbors(20)
-        c.calculate_target_covariances(REG_PLANE)
-        c.create_target_voxelmap()
-        c.set_cloud_device("source", sp + pi * n_s * 12, n_s, 12)
-        c.find_source_neighbors(20)
-        c.calculate_source_covariances(REG_PLANE)
-        return c.align()
+        # vgicp_register = clear + setInputTarget (kNN, covariances, voxel map) + setInputSource (kNN, covariances) + align in one
+        # C call: the body of the reference's benchmark loop (src/align.cpp:72-81), no Python between the stages
+        return c.register_raw(tp + pi * n_t * 12, n_t, sp + pi * n_s * 12, n_s, 12, True, 20, REG_PLANE)
 
     def step_e2e(ci=0, pi=0):
         """The same through the reference-facing class, host (pinned) buffers in, aligned cloud + pose out (align.cpp:72-81)."""

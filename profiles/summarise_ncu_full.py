@@ -26,7 +26,7 @@ WANT = {
     "sm__cycles_elapsed.avg": "sm_cycles_elapsed",
     "smsp__issue_active.avg.per_cycle_active": "issue_per_cycle_active",
 }
-CATEGORY = (("k_linearize<27, 0", "compute_error"), ("k_linearize<27, 1", "linearize"), ("k_linearize<", "linearize_other"), ("k_knn_grid_heavy", "knn_heavy"), ("k_knn_grid", "knn"),
+CATEGORY = (("k_linearize_spec", "linearize"), ("k_linearize<27, 0", "compute_error"), ("k_linearize<27, 1", "linearize"), ("k_linearize<", "linearize_other"), ("k_knn_grid_heavy", "knn_heavy"), ("k_knn_grid", "knn"),
             ("k_covariance_knn", "covariance"), ("k_table_insert", "voxelmap_build"))
 
 
