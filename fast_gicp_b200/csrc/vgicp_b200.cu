@@ -406,6 +406,7 @@ int voxelmap_finish(vgicp_handle h, Cloud& t, VoxelMap& m) {
   m.pending = false;
   m.num_buckets = B;
   const int vmax = n < B ? n : B;  // upper bound on the number of voxels: buffers are sized for it, the exact count arrives later
+  if (vmax > (1 << 27)) { m.pending = false; return fail(h, VGICP_ERR_INVALID_ARGUMENT, "create_target_voxelmap: more than 2^27 voxels (the evaluation kernels pack a voxel id in 27 bits)"); }
   CU_TRY(h, m.buckets.reserve(B));
   CU_TRY(h, m.vox.reserve(vmax));
   CU_TRY(h, m.sums.reserve((size_t)vmax * 10));
