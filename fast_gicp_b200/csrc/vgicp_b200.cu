@@ -516,8 +516,8 @@ LinLaunch make_lin_launch(vgicp_handle h) {
   a.Tlin = h->lin; a.Teval = h->lin;
   a.partials = h->partials.p; a.ticket = h->d_ticket; a.out = h->d_out;
   a.done_flag = nullptr; a.done_seq = 0;
-  // lanes per source point: split the neighbour cells of a point over G lanes while the cloud is too small to fill the
-  // GPU with one thread per point (latency-bound regime); one lane per point once it is large (ALU/bandwidth-bound regime)
+  // lanes per source point in the lookup phase: split the neighbour cells of a point over G lanes while the cloud is too small to
+  // fill the GPU with one thread per point (latency-bound regime); one lane per point once it is large
   const int n_off = a.n_off;
   const bool wide = a.n < 400000 && n_off > 1;
   // small clouds: split a point's cells over 3 (DIRECT27: whole z-columns), 4 (<= 7 offsets) or 8 lanes.  With the hits compacted

@@ -752,10 +752,9 @@ __device__ __forceinline__ void lin_unpack(const double* s, double* out) {
   }
 }
 
-// MODE: 0 = offsets from memory (DIRECT_RADIUS or anything), 1 / 7 / 27 = the reference's fixed tables.
-// G lanes share one source point and split its neighbour cells (lane s takes offsets s, s+G, ...): at 17k points a
-// one-thread-per-point mapping leaves one warp per scheduler and 27 serial dependent probes per thread; with G = 8 the
-// probes of a lane (<= 4) are issued together and the grid has 8x the warps to hide the L2 latency.
+// One evaluation (update_correspondences + compute_error fused).  MODE: 0 = offsets from memory (DIRECT_RADIUS or anything),
+// 1 / 7 / 27 = the reference's fixed tables; G = lanes per source point in the lookup phase (see lin_accumulate_impl): at 17k points
+// a one-thread-per-point mapping would leave one warp per scheduler with 27 serial dependent lookups per thread.
 template <int MODE, bool WANT_H, int G>
 __global__ void __launch_bounds__(kLinThreads) k_linearize(const LinArgs a) {
   constexpr int NV = WANT_H ? kLinValues : 1;
