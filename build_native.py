@@ -67,6 +67,22 @@ def build_native(force=False, verbose=False):
     return LIB_PATH
 
 
+PREP_SRC = os.path.join(CSRC, "prep", "vgicp_prep.cu")
+PREP_LIB_PATH = os.path.join(LIB_DIR, "libvgicp_prep_b200.so")
+
+
+def build_prep(force=False):
+    """Input-preparation library (include/vgicp_prep_b200.h): lib/libvgicp_prep_b200.so, independent of libvgicp_b200.so."""
+    hdr = os.path.join(ROOT, "include", "vgicp_prep_b200.h")
+    if not force and os.path.exists(PREP_LIB_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(PREP_LIB_PATH) for d in (PREP_SRC, hdr)):
+        return PREP_LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    ccbin = ["-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"]
+    subprocess.check_call([_nvcc()] + NVCC_FLAGS + ccbin + ["-I", os.path.join(ROOT, "include"), "-shared", "-o", PREP_LIB_PATH, PREP_SRC], env=env)
+    return PREP_LIB_PATH
+
+
 def build_host_cpp(force=False):
     """C++ host side above the C ABI: the pygicp pybind11 module (fast_gicp_b200/lib/pygicp*.so) and the C++ alignment test
     (fast_gicp_b200/lib/gicp_test), both linked against libvgicp_b200.so with an $ORIGIN rpath."""
@@ -101,3 +117,4 @@ def build_host_cpp(force=False):
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_host_cpp(force="--force" in sys.argv))
+    print(build_prep(force="--force" in sys.argv))

@@ -94,6 +94,8 @@ def lib():
         L.orc64_covariances.argtypes = [fp, C.c_int, C.c_int, C.c_int, dp, C.c_int]
         L.orc64_align.argtypes = [fp, dp, C.c_int, fp, dp, C.c_int, C.c_double, ip, C.c_int, C.POINTER(LsqParams), dp, C.c_int, C.POINTER(LsqResult)]
         L.orc_num_threads.restype = C.c_int
+        L.orc_remove_near_origin.argtypes = [fp, C.c_int, fp]
+        L.orc_approximate_voxel_grid.argtypes = [fp, C.c_int, C.c_float, C.c_int, fp]
         _lib = L
     return _lib
 
@@ -349,6 +351,22 @@ def align_f64(target, tgt_cov, source, src_cov, res=1.0, offs=None, guess=None, 
     lib().orc64_align(_p(target, C.c_float), _p(tgt_cov, C.c_double), len(target), _p(source, C.c_float), _p(src_cov, C.c_double), len(source), float(res), _p(offs, C.c_int),
                       len(offs), C.byref(params), _p(g, C.c_double), threads, C.byref(r))
     return AlignResult(r)
+
+
+def remove_near_origin(pts):
+    """src/align.cpp:128-133: drop points with squaredNorm() < 1e-3 (stable)."""
+    p = _f32(np.asarray(pts)[:, :3])
+    out = np.empty_like(p)
+    m = lib().orc_remove_near_origin(_p(p, C.c_float), len(p), _p(out, C.c_float))
+    return out[:m].copy()
+
+
+def approximate_voxel_grid(pts, leaf, histsize=512):
+    """pcl::ApproximateVoxelGrid<PointXYZ> restated (align.cpp:136-147, kitti.cpp:80-82, python/main.cpp:46-62)."""
+    p = _f32(np.asarray(pts)[:, :3])
+    out = np.empty_like(p)
+    m = lib().orc_approximate_voxel_grid(_p(p, C.c_float), len(p), C.c_float(leaf), int(histsize), _p(out, C.c_float))
+    return out[:m].copy()
 
 
 def se3_exp(a):

@@ -1328,3 +1328,59 @@ ORC_API int orc_num_threads(void) {
   return 1;
 #endif
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Input preparation: what the reference's callers do to a raw scan before setInputTarget/Source.
+ * ------------------------------------------------------------------------------------------------------------------- */
+
+/* src/align.cpp:128-133 : erase(remove_if(squaredNorm() < 1e-3)) -- stable, float arithmetic ((x*x + y*y) + z*z as Eigen's
+ * unrolled redux evaluates a 3-vector).  out may alias xyz.  Returns the number of points kept. */
+ORC_API int orc_remove_near_origin(const float* xyz, int n, float* out) {
+  int m = 0;
+  for (int i = 0; i < n; i++) {
+    const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    const float sq = (x * x + y * y) + z * z;
+    if (sq < 1e-3f) continue;
+    out[3 * m] = x; out[3 * m + 1] = y; out[3 * m + 2] = z;
+    m++;
+  }
+  return m;
+}
+
+/* pcl::ApproximateVoxelGrid<PointXYZ>::applyFilter (src/align.cpp:136-147, src/kitti.cpp:80-82, src/python/main.cpp:46-62,81-91).
+ * PCL is not vendored: restated from the published algorithm (pcl/filters/impl/approximate_voxel_grid.hpp) -- a streaming
+ * filter with a `histsize`-entry (default 512) hash history; a point goes to entry (ix*7171 + iy*3079 + iz*4231) & (histsize-1)
+ * with ix = floor(x * inverse_leaf) in float; an entry holding a different voxel is flushed (centroid emitted) first; the
+ * remaining entries are flushed in entry order at the end.  Centroids accumulate in float in input order.
+ * Pinned by the point counts the reference prints (README.md:116: 17249 / 17518 for the data/ pair), tests/test_oracle_golden.py.
+ * out: capacity n points.  Returns the number of output points. */
+ORC_API int orc_approximate_voxel_grid(const float* xyz, int n, float leaf, int histsize, float* out) {
+  typedef struct { int ix, iy, iz, count; float sx, sy, sz; } He;
+  He* hist = (He*)calloc((size_t)histsize, sizeof(He));
+  const float inv = 1.0f / leaf;
+  int m = 0;
+  for (int i = 0; i < n; i++) {
+    const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    const int ix = (int)floorf(x * inv), iy = (int)floorf(y * inv), iz = (int)floorf(z * inv);
+    const long long hl = (long long)ix * 7171 + (long long)iy * 3079 + (long long)iz * 4231;
+    He* h = &hist[(size_t)(hl & (long long)(histsize - 1))];
+    if (h->count && (h->ix != ix || h->iy != iy || h->iz != iz)) {
+      const float c = (float)h->count;
+      out[3 * m] = h->sx / c; out[3 * m + 1] = h->sy / c; out[3 * m + 2] = h->sz / c;
+      m++;
+      h->count = 0; h->sx = h->sy = h->sz = 0.0f;
+    }
+    h->ix = ix; h->iy = iy; h->iz = iz;
+    h->count++;
+    h->sx += x; h->sy += y; h->sz += z;
+  }
+  for (int s = 0; s < histsize; s++) {
+    He* h = &hist[s];
+    if (!h->count) continue;
+    const float c = (float)h->count;
+    out[3 * m] = h->sx / c; out[3 * m + 1] = h->sy / c; out[3 * m + 2] = h->sz / c;
+    m++;
+  }
+  free(hist);
+  return m;
+}

@@ -1,0 +1,146 @@
+"""Input preparation: near-origin filter + pcl::ApproximateVoxelGrid.
+
+CPU part: the oracle restatement against the reference's goldens and against the numpy restatement that made the fixtures; the
+parallel formulation the CUDA kernels implement (512 independent history chains, flushed centroids ranked by the index of the
+flushing point) against the serial filter; the C ABI surface of lib/libvgicp_prep_b200.so.
+GPU part (-m gpu): the CUDA library against the oracle, bit for bit.  It has not run on hardware yet (the round-1 GPU budget
+was spent before it was written), so it is expected-to-fail-tolerant (xfail, non-strict) and runs in a child process: a fault
+there cannot poison the CUDA context of the other GPU tests.  Round 2 turns it into a hard test."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, GOLDEN)
+REF_DATA = "/root/reference/data"
+
+
+def raw_like_cloud(seed, n=40000):
+    """A scan-ordered cloud with duplicates at the origin (invalid returns) and a long run of points in one voxel."""
+    rng = np.random.default_rng(seed)
+    az = np.sort(rng.uniform(-np.pi, np.pi, n))
+    r = rng.uniform(2.0, 60.0, n) * (1.0 + 0.3 * np.sin(5 * az))
+    pts = np.stack([r * np.cos(az), r * np.sin(az), rng.normal(0.0, 0.8, n) - 1.2], axis=1).astype(np.float32)
+    pts[rng.choice(n, n // 15, replace=False)] = 0.0  # invalid returns, scattered
+    if n > 1400:
+        pts[1000:1400] = 0.0                          # ... and a long run of them
+    if n > 5300:
+        pts[5000:5300] = pts[5000] + rng.normal(0, 0.003, (300, 3)).astype(np.float32)  # > 16 matches of one entry in one tile
+    return pts
+
+
+def parallel_formulation(pts, leaf, remove_near_origin):
+    """What fast_gicp_b200/csrc/prep/vgicp_prep.cu computes, restated with numpy bookkeeping: per history entry an independent
+    sequential chain over the points that hash to it; a flushed centroid is stored at the index of the point that flushed it;
+    output = those centroids by index, then the entries still holding a voxel in entry order."""
+    p = pts.astype(np.float32)
+    inv = np.float32(1.0) / np.float32(leaf)
+    ijk = np.floor(p * inv).astype(np.int64)
+    entry = (ijk[:, 0] * 7171 + ijk[:, 1] * 3079 + ijk[:, 2] * 4231) & 511
+    if remove_near_origin:
+        sq = (p[:, 0] * p[:, 0] + p[:, 1] * p[:, 1]) + p[:, 2] * p[:, 2]
+        entry = np.where(sq < np.float32(1e-3), -1, entry)
+    flushed = {}
+    tail = []
+    for h in range(512):
+        idx = np.flatnonzero(entry == h)
+        key, cnt, s = None, 0, np.zeros(3, np.float32)
+        for i in idx:
+            k = tuple(ijk[i])
+            if cnt and k != key:
+                flushed[i] = s / np.float32(cnt)
+                cnt, s = 0, np.zeros(3, np.float32)
+            key = k
+            cnt += 1
+            s = s + p[i]
+        if cnt:
+            tail.append(s / np.float32(cnt))
+    out = [flushed[i] for i in sorted(flushed)] + tail
+    return np.asarray(out, dtype=np.float32).reshape(-1, 3)
+
+
+# ------------------------------------------------------------------------------------------------------------------ CPU
+def test_oracle_matches_the_numpy_restatement_and_the_fixture():
+    import make_fixtures as mf
+
+    pts = raw_like_cloud(1, 20000)
+    for leaf in (0.1, 0.25, 1.0):
+        assert np.array_equal(O.approximate_voxel_grid(pts, leaf), mf.approximate_voxel_grid(pts, leaf))
+    kept = O.remove_near_origin(pts)
+    assert np.array_equal(kept, mf.remove_near_origin(pts))
+    assert len(kept) < len(pts) and not (np.abs(kept).sum(axis=1) == 0).any()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DATA), reason="needs the reference's data/ directory (build container only)")
+def test_oracle_pinned_by_the_reference_goldens():
+    """README.md:116 prints target:17249 source:17518 for the data/ pair (produced before align.cpp gained its origin filter);
+    with the filter (current align.cpp protocol) the result is the committed benchmark fixture, bit for bit."""
+    import make_fixtures as mf
+
+    tgt = mf.read_pcd_xyz(os.path.join(REF_DATA, "251370668.pcd"))
+    src = mf.read_pcd_xyz(os.path.join(REF_DATA, "251371071.pcd"))
+    assert (len(O.approximate_voxel_grid(tgt, 0.1)), len(O.approximate_voxel_grid(src, 0.1))) == (17249, 17518)
+    d = np.load(os.path.join(GOLDEN, "pair_0p1.npz"))
+    assert np.array_equal(O.approximate_voxel_grid(O.remove_near_origin(tgt), 0.1), d["target"])
+    assert np.array_equal(O.approximate_voxel_grid(O.remove_near_origin(src), 0.1), d["source"])
+
+
+@pytest.mark.parametrize("flt", [False, True])
+def test_parallel_formulation_equals_the_serial_filter(flt):
+    pts = raw_like_cloud(2, 12000)
+    want = O.approximate_voxel_grid(O.remove_near_origin(pts) if flt else pts, 0.25)
+    assert np.array_equal(parallel_formulation(pts, 0.25, flt), want)
+
+
+def test_prep_library_exports_its_abi():
+    import ctypes
+
+    import build_native
+
+    path = build_native.build_prep()
+    from fast_gicp_b200 import prep
+
+    lib = ctypes.CDLL(path)
+    hdr = open(os.path.join(ROOT, "include", "vgicp_prep_b200.h")).read()
+    for sym in prep.EXPORTED_SYMBOLS:
+        assert hasattr(lib, sym) and sym + "(" in hdr
+    import re
+
+    declared = set(re.findall(r"VGICP_PREP_API\s+[\w\s\*]+?\b(vgicp_prep_\w+)\s*\(", hdr))
+    assert declared == set(prep.EXPORTED_SYMBOLS)
+
+
+# ------------------------------------------------------------------------------------------------------------------ GPU
+_CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+sys.path.insert(0, %r)
+import oracle as O
+from fast_gicp_b200.prep import InputPrep
+from test_input_prep import raw_like_cloud
+p = InputPrep(0)
+d = np.load(%r)
+clouds = [raw_like_cloud(3), raw_like_cloud(4, 3000), raw_like_cloud(5, 2048), raw_like_cloud(6, 1), np.repeat(d["target"], 4, axis=0)]
+for c in clouds:
+    for leaf, flt in ((0.1, True), (0.25, False), (1.0, True)):
+        got = p.approximate_voxel_grid(c, leaf, flt)
+        want = O.approximate_voxel_grid(O.remove_near_origin(c) if flt else c, leaf)
+        assert got.shape == want.shape, (got.shape, want.shape)
+        assert np.array_equal(got, want)
+assert len(p.approximate_voxel_grid(np.zeros((0, 3), np.float32), 0.1)) == 0
+print("prep ok")
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="CUDA input-prep kernels not yet run on hardware (written after the round-1 GPU budget was spent)")
+def test_gpu_input_prep_matches_the_oracle_bit_for_bit():
+    code = _CHILD % (ROOT, os.path.join(ROOT, "tests"), os.path.join(GOLDEN, "pair_0p2.npz"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "prep ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
