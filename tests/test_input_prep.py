@@ -65,6 +65,51 @@ def parallel_formulation(pts, leaf, remove_near_origin):
     return np.asarray(out, dtype=np.float32).reshape(-1, 3)
 
 
+# k_prep_walk's bookkeeping restated step by step: tiles of 2048 staged points, per-entry lists of <= 16 tile-local indices
+# filled in ARBITRARY order (shared-memory atomics) and sorted back, the scan fallback for longer runs, flushes stored at the
+# flushing point's index
+kHist, kTile, kCap = 512, 2048, 16
+def emulate_walk_kernel(pts, leaf, flt, seed=0):
+    rng = np.random.default_rng(seed)
+    p = pts.astype(np.float32); n = len(p)
+    inv = np.float32(1.0)/np.float32(leaf)
+    ijk = np.floor(p*inv).astype(np.int64)
+    ent = ((ijk[:,0]*7171 + ijk[:,1]*3079 + ijk[:,2]*4231) & 511).astype(np.int64)
+    if flt:
+        sq = (p[:,0]*p[:,0] + p[:,1]*p[:,1]) + p[:,2]*p[:,2]
+        ent = np.where(sq < np.float32(1e-3), 0xFFFF, ent)
+    flushed = np.zeros((n,4), np.float32)
+    E = [dict(k=None,c=0,s=np.zeros(3,np.float32)) for _ in range(kHist)]
+    def step(e,i):
+        k = tuple(ijk[i])
+        if e['c'] and e['k'] != k:
+            flushed[i,:3] = e['s']/np.float32(e['c']); flushed[i,3] = 1
+            e['c'] = 0; e['s'] = np.zeros(3,np.float32)
+        e['k'] = k; e['c'] += 1; e['s'] = e['s'] + p[i]
+    for base in range(0, n, kTile):
+        cnt = np.zeros(kHist, int); lst = np.full((kHist,kCap), -1, int)
+        sh = np.full(kTile, 0xFFFF, int)
+        order = rng.permutation(kTile)   # arbitrary arrival order of the atomics
+        for j in order:
+            i = base + j
+            t = ent[i] if i < n else 0xFFFF
+            sh[j] = t
+            if t != 0xFFFF:
+                q = cnt[t]; cnt[t] += 1
+                if q < kCap: lst[t,q] = j
+        for h in range(kHist):
+            c = cnt[h]
+            if 0 < c <= kCap:
+                for j in sorted(lst[h,:c]): step(E[h], base+j)
+            elif c > kCap:
+                for j in range(kTile):
+                    if sh[j] == h: step(E[h], base+j)
+    out = [flushed[i,:3] for i in range(n) if flushed[i,3] != 0]
+    for h in range(kHist):
+        if E[h]['c']: out.append(E[h]['s']/np.float32(E[h]['c']))
+    return np.asarray(out, np.float32).reshape(-1,3)
+
+
 # ------------------------------------------------------------------------------------------------------------------ CPU
 def test_oracle_matches_the_numpy_restatement_and_the_fixture():
     import make_fixtures as mf
@@ -96,6 +141,13 @@ def test_parallel_formulation_equals_the_serial_filter(flt):
     pts = raw_like_cloud(2, 12000)
     want = O.approximate_voxel_grid(O.remove_near_origin(pts) if flt else pts, 0.25)
     assert np.array_equal(parallel_formulation(pts, 0.25, flt), want)
+
+
+@pytest.mark.parametrize("n,leaf,flt", [(1, 0.1, True), (2048, 1.0, False), (9000, 0.1, True), (9000, 1.0, False)])
+def test_walk_kernel_bookkeeping_equals_the_serial_filter(n, leaf, flt):
+    c = raw_like_cloud(n + 7, n)  # n = 9000 holds both the origin run and a > 16-point run of one entry (scan fallback)
+    want = O.approximate_voxel_grid(O.remove_near_origin(c) if flt else c, leaf)
+    assert np.array_equal(emulate_walk_kernel(c, leaf, flt), want)
 
 
 def test_prep_library_exports_its_abi():
