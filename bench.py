@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- registrations/sec of the VGICP hot path on B200 (BASELINE.json metric), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2_direct1|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2_direct1|c3|c4|c4_direct1|c5]
 
 Workload (N=1 default, BASELINE configs[1]): the reference's benchmark pair (tests/golden/pair_0p1.npz = data/251370668.pcd
 vs 251371071.pcd after align.cpp's filter + ApproximateVoxelGrid(0.1): 17047 / 17334 points), FastVGICPCuda, DIRECT27,
@@ -61,9 +61,10 @@ def load_workload(name):
         t, s, _ = kitti_like_pair(beams=64, az_steps=2083, seed=1000, pose=(0.8, 0.05, 0.7), downsample=0.25)
         return dict(name="C5: NDTCuda D2D DIRECT7 res=1.0, synthetic HDL-64 pair (0.25 m downsample)", target=t, source=s, method="DIRECT7", res=1.0, data="synthetic",
                     problem="ndt_d2d")
-    if name == "c4":
+    if name in ("c4", "c4_direct1"):
         t, s, _ = kitti_like_pair(beams=128, az_steps=8192, seed=44, pose=(0.5, 0.0, 1.0), downsample=0.0, max_points=1_000_000)
-        return dict(name="C4: synthetic 1M-pt pair DIRECT27 res=0.5", target=t, source=s, method="DIRECT27", res=0.5, data="synthetic")
+        method = "DIRECT27" if name == "c4" else "DIRECT1"  # DIRECT1: the bandwidth-bound configuration of the evaluation kernel
+        return dict(name="C4: synthetic 1M-pt pair %s res=0.5" % method, target=t, source=s, method=method, res=0.5, data="synthetic")
     raise SystemExit("unknown workload " + name)
 
 
