@@ -30,7 +30,7 @@ def main():
         from fast_gicp_b200.synthetic import kitti_like_pair
 
         tgt, src, _ = kitti_like_pair(beams=128, az_steps=8192, seed=44, pose=(0.5, 0.0, 1.0), downsample=0.0, max_points=1_000_000)
-        res, method = 0.5, "DIRECT27"
+        res, method = 0.5, os.environ.get("VGICP_C4_METHOD", "DIRECT27")  # DIRECT1: the bandwidth-bound configuration
 
     def prepare(c):
         c.set_resolution(res)
