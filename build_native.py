@@ -83,6 +83,23 @@ def build_prep(force=False):
     return PREP_LIB_PATH
 
 
+BATCH_SRC = os.path.join(CSRC, "batch", "vgicp_batch.cpp")
+BATCH_LIB_PATH = os.path.join(LIB_DIR, "libvgicp_batch_b200.so")
+
+
+def build_batch(force=False):
+    """Batch registration library (include/vgicp_batch_b200.h): host-only C++ over the C ABI, lib/libvgicp_batch_b200.so."""
+    build_native(force=False)
+    hdrs = [os.path.join(ROOT, "include", "vgicp_batch_b200.h"), os.path.join(ROOT, "include", "vgicp_b200.h"), LIB_PATH]
+    if not force and os.path.exists(BATCH_LIB_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(BATCH_LIB_PATH) for d in [BATCH_SRC] + hdrs):
+        return BATCH_LIB_PATH
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.check_call([gxx, "-shared", "-fPIC", "-fvisibility=hidden", "-std=c++17", "-O2", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), BATCH_SRC, "-o", BATCH_LIB_PATH,
+                           "-L", LIB_DIR, "-Wl,-rpath,$ORIGIN", "-lvgicp_b200"], env=env)
+    return BATCH_LIB_PATH
+
+
 def build_host_cpp(force=False):
     """C++ host side above the C ABI: the pygicp pybind11 module (fast_gicp_b200/lib/pygicp*.so) and the C++ alignment test
     (fast_gicp_b200/lib/gicp_test), both linked against libvgicp_b200.so with an $ORIGIN rpath."""
@@ -118,3 +135,4 @@ if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_host_cpp(force="--force" in sys.argv))
     print(build_prep(force="--force" in sys.argv))
+    print(build_batch(force="--force" in sys.argv))
