@@ -568,3 +568,28 @@ def test_rbf_covariances_against_numpy():
         want = (s2 - np.outer(mean, s1)) / sw
         assert np.abs(got[i] - want).max() < 2e-4 * max(1.0, np.abs(want).max()), i
     c.close()
+
+
+# ----------------------------------------------------------------------------- getFitnessScore
+@pytest.mark.xfail(strict=False, reason="numerical check added after the round-1 GPU budget was spent; not yet run on hardware")
+def test_fitness_score_against_kdtree(prepared, relative_pose):
+    """pcl::Registration::getFitnessScore(max_range): mean squared nearest-neighbour distance of the transformed source over the
+    pairs with d^2 <= max_range (PCL compares the SQUARED distance with max_range)."""
+    from scipy.spatial import cKDTree
+
+    from fast_gicp_b200.core import Core
+
+    c = Core(0)
+    c.set_target_cloud(prepared["tgt"])
+    c.set_source_cloud(prepared["src"])
+    tree = cKDTree(prepared["tgt"].astype(np.float64))
+    for T in (np.eye(4), relative_pose):
+        Tf = T.astype(np.float32)
+        p = (prepared["src"].astype(np.float32) @ Tf[:3, :3].T + Tf[:3, 3]).astype(np.float64)
+        d, _ = tree.query(p, k=1)
+        d2 = d * d
+        assert abs(c.fitness_score(T) - d2.mean()) <= 1e-4 * d2.mean()
+        for max_range in (0.05, 0.5):
+            m = d2 <= max_range
+            assert abs(c.fitness_score(T, max_range) - d2[m].mean()) <= 1e-3 * d2[m].mean()
+    c.close()
