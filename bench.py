@@ -210,6 +210,9 @@ def main():
                     help="concurrent registration streams per GPU (host thread + handle each); default 16, or 8 when more than 2 ranks share the host "
                          "(every stream's thread spins on its completion word)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-impl", default="class", choices=["class", "batch"],
+                    help="end-to-end arm: the FastVGICPCuda class from S Python threads (default, verified), or one vgicp_batch_register C call per timed region "
+                         "(include/vgicp_batch_b200.h; not yet verified on hardware)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -364,12 +367,40 @@ def main():
 
     # ---- e2e: host buffers through the reference-facing class, S concurrent streams
     note("value arm done")
-    run_streams(step_e2e, e2e_streams, W)
-    barrier()
-    l1 = sum(r.vgicp_cuda_.launch_count() for r in regs)
-    total_ms_e2e, T_e2e = run_streams(step_e2e, e2e_streams, K)
-    barrier()
-    launches_e2e = sum(r.vgicp_cuda_.launch_count() for r in regs) - l1
+    e2e_api = "FastVGICPCuda.setInputTarget/setInputSource/align (pinned host buffers, aligned cloud + pose read back)"
+    if args.e2e_impl == "batch" and not ndt:
+        # one C call for all S*K registrations: a pool of S handles + worker threads inside libvgicp_batch_b200.so, pinned host buffers in,
+        # aligned clouds + poses out; device time = events on the current stream around the (blocking) call
+        from fast_gicp_b200.batch import BatchRegistration
+
+        pool = BatchRegistration(local_rank, S)
+        pool.configure(w["res"], w["method"])
+        aligned_all = [torch.empty((n_s, 3), dtype=torch.float32).pin_memory().numpy() for _ in range(S * max(K, W))]
+
+        def run_batch(steps):
+            idx = [(ci + j * S) % P for j in range(steps) for ci in range(S)]
+            call = pool.prepare([pool_t_np[i] for i in idx], [pool_s_np[i] for i in idx], aligned_all[: len(idx)])
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record()
+            res_b = call(20, REG_PLANE)
+            ev1.record()
+            torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1), pose_from_c(res_b[0].T)
+
+        run_batch(W)
+        barrier()
+        total_ms_e2e, T_e2e = run_batch(K)
+        barrier()
+        launches_e2e = int(launches)  # the pool's handles are internal: same launches per registration as the resident arm
+        e2e_api = "vgicp_batch_register (one C call for all registrations of the timed region; pinned host buffers, aligned clouds + poses read back)"
+    else:
+        run_streams(step_e2e, e2e_streams, W)
+        barrier()
+        l1 = sum(r.vgicp_cuda_.launch_count() for r in regs)
+        total_ms_e2e, T_e2e = run_streams(step_e2e, e2e_streams, K)
+        barrier()
+        launches_e2e = sum(r.vgicp_cuda_.launch_count() for r in regs) - l1
     clocks = sampler.stop() if sampler else None
 
     # ---- single-stream latency (the reference's sequential protocol), L2 flushed between registrations
@@ -492,7 +523,7 @@ def main():
                    "parallelism": "replicas x%d" % world, "n_target": n_t, "n_source": n_s, "num_voxels": V, "num_buckets": B,
                    "lm_iterations": int(res.nr_iterations) + 1, "evaluations": int(res.n_linearize + res.n_compute_error), "converged": bool(res.converged)},
         "e2e": {"value": world * S * K / (total_ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * S, "d2h_bytes_per_step": d2h * S, "ms_per_step": total_ms_e2e / K,
-                "api": "FastVGICPCuda.setInputTarget/setInputSource/align (pinned host buffers, aligned cloud + pose read back)"},
+                "api": e2e_api},
         "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
         "roofline": roofline, "roofline_other_kernels": roofline_other, "cpu_baseline": cpu_baseline, "clocks": clocks, "per_kernel": per_kernel,
         "single_stream": {"ms_per_registration": float(np.mean(lat)), "registrations_per_s": 1e3 / float(np.mean(lat)),

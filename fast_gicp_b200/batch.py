@@ -63,6 +63,29 @@ class BatchRegistration:
     def configure(self, resolution=1.0, method="DIRECT1", radius=-1.0):
         self._check(self._lib.vgicp_batch_configure(self._b, float(resolution), int(_core.NEIGHBOR_SEARCH[method] if isinstance(method, str) else method), float(radius)))
 
+    def prepare(self, targets, sources, aligned_out=None):
+        """Build the pointer tables of a batch once (arrays must stay alive and C-contiguous float32; aligned_out: optional list of
+        (n_i, 3) float32 host buffers, e.g. pinned).  Returns a callable running the batch: call() -> (first status, results)."""
+        n = len(targets)
+        assert len(sources) == n and (aligned_out is None or len(aligned_out) == n)
+        for a in list(targets) + list(sources) + list(aligned_out or []):
+            assert a.dtype == np.float32 and a.flags.c_contiguous and a.ndim == 2 and a.shape[1] == 3
+        vp = C.c_void_p
+        tp = (vp * n)(*[a.ctypes.data for a in targets])
+        sp = (vp * n)(*[a.ctypes.data for a in sources])
+        nt = (C.c_size_t * n)(*[len(a) for a in targets])
+        ns = (C.c_size_t * n)(*[len(a) for a in sources])
+        ap = (vp * n)(*[a.ctypes.data for a in aligned_out]) if aligned_out is not None else None
+        res = (_core.AlignResult * n)()
+        keep = (targets, sources, aligned_out)
+
+        def call(k=20, reg=_core.REG_PLANE):
+            _ = keep
+            self._check(self._lib.vgicp_batch_register(self._b, n, tp, nt, sp, ns, 12, 0, int(k), int(reg), None, None, res, ap))
+            return res
+
+        return call
+
     def register(self, targets, sources, k=20, reg=_core.REG_PLANE, guesses=None, params=None, want_aligned=False):
         """targets / sources: sequences of (n_i, 3) float32 C-contiguous host arrays.  Returns (list of 4x4 poses, list of
         AlignResult, list of aligned clouds or None)."""

@@ -40,3 +40,8 @@ echo "== prep: $(tail -1 gpurun_out/r2_prep_timing.log)"
 timeout 400 python bench.py > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
 python -c "
 import json; d = json.load(open('gpurun_out/r2_bench.json')); print('== bench: value', round(d['value']), 'e2e', round(d['e2e']['value']), 'single-stream ms', round(d['single_stream']['ms_per_registration'], 3))"
+# 7. the end-to-end arm through vgicp_batch_register (one C call per timed region) next to the default class-based arm
+timeout 400 python bench.py --e2e-impl batch --no-cpu-baseline > gpurun_out/r2_bench_batch.json 2> gpurun_out/r2_bench_batch.err
+python -c "
+import json; d = json.load(open('gpurun_out/r2_bench_batch.json')); print('== bench --e2e-impl batch: value', round(d['value']), 'e2e', round(d['e2e']['value']), d['pose_check'])"
+
