@@ -225,8 +225,10 @@ def main():
         run_reference_arm(args, w, rank, world)
         return
 
+    print("[bench] importing torch (the first import on a fresh box pages the image in and can take minutes)", file=sys.stderr, flush=True)
     import torch
 
+    print("[bench] torch imported", file=sys.stderr, flush=True)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
