@@ -143,8 +143,10 @@ typedef struct {
 } vgicp_align_result;
 
 VGICP_API void vgicp_lsq_default_params(vgicp_lsq_params* p);
-/* Whole LsqRegistration::computeTransformation loop (lsq_registration_impl.hpp:53-79,106-168) run device-resident:
- * same linearize / compute_error evaluations, same LM logic in double, no host round trip per evaluation. */
+/* Whole LsqRegistration::computeTransformation loop (lsq_registration_impl.hpp:53-79,106-168) inside the library: the same
+ * linearize / compute_error evaluations and the same LM / GN logic in double, without crossing the ABI once per evaluation.
+ * Driven from the host by default (one 344-byte result per evaluation through mapped memory); vgicp_set_align_mode selects the
+ * device-resident state machine, vgicp_set_speculation the fused trial evaluation.  result->T = final_transformation_. */
 VGICP_API int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* params, vgicp_align_result* result);
 /* One whole registration: clearTarget/clearSource + setInputTarget + setInputSource + align (the body of the reference's
  * benchmark loop, src/align.cpp:72-81) with GPU k-NN covariances.  xyz are host pointers, or device pointers when on_device != 0. */
