@@ -72,7 +72,7 @@ struct VoxelMap {
   bool v_pending = false;  // num_voxels still in flight
   cudaEvent_t ev_attempt = nullptr, ev_done = nullptr;
   int ndt = 0;             // 1: built from the points alone + MIN_EIG (NDT), 0: from points + covariances (VGICP)
-  int* d_counters = nullptr;  // [0] fail count, [1] num_voxels, [2..4] / [5..7] min / max voxel coordinate
+  int* d_counters = nullptr;  // [0] fail count, [1] num_voxels, [2..4] / [5..7] min / max voxel coordinate, [8] set_neighbors verdict
   int* h_counters = nullptr;  // pinned
   DevBuf<unsigned long long> chunk_state;  // k_table_assign_ids look-back (epoch-tagged block totals)
   unsigned chunk_epoch = 0;
@@ -130,6 +130,7 @@ struct vgicp_context {
   int align_mode = 1;  // 1 = host-driven loop over the evaluation kernels (default: faster today), 0 = device-resident LM chain
   LmState* d_lm = nullptr;
   LmState* h_lm = nullptr;  // pinned
+  int force_lin_g = 0;  // VGICP_LIN_G override of the lanes-per-point split (experiments)
   int knn_mode = 0;  // 0 = hash grid (default), 1 = warp-cooperative scan of the whole cloud, 2 = legacy per-thread scan
   DevBuf<double> partials;
   DevBuf<int> corr_ids;
@@ -228,7 +229,13 @@ Pose to_pose(const double* T) {  // Eigen::Isometry3d (column-major) -> float im
 }
 
 int set_cloud(vgicp_handle h, Cloud& c, const float* xyz, size_t n, size_t stride, bool on_device = false) {
-  h->ndt_ready = false;  // NDT voxel maps are rebuilt lazily from the new points (ndt_cuda.cu:104,114 reset the maps)
+  // NDT: set_{source,target}_cloud resets that cloud's voxel map only (ndt_cuda.cu:104,114); it is rebuilt by the next create_voxelmaps
+  h->ndt_ready = false;
+  {
+    VoxelMap& nm = (&c == &h->target) ? h->ndt_t : h->ndt_s;
+    nm.built = false;
+    nm.pending = false;
+  }
   if (n > 0 && !xyz) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_cloud: null points");
   if (stride < 12 || (stride % 4) != 0) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_cloud: stride_bytes must be a multiple of 4 and >= 12");
   if (n > (size_t)0x7fffffff / 64) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_cloud: too many points");
@@ -259,7 +266,18 @@ int set_neighbors(vgicp_handle h, Cloud& c, int k, const int* idx, size_t nk) {
   if (k <= 0 || !idx || nk != (size_t)k * (size_t)c.n) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_neighbors: k * num_points != neighbors.size()");
   CU_TRY(h, c.nbr.reserve(nk));
   CU_TRY(h, cudaMemcpyAsync(c.nbr.p, idx, nk * sizeof(int), cudaMemcpyHostToDevice, c.st));
+  // an index outside [0, n) would be an illegal address in k_covariance_knn and poison the context of every handle of the process:
+  // one pass over the table, the verdict comes back with the synchronisation the copy needs anyway
+  int* bad = h->map.d_counters + 8;
+  CU_TRY(h, cudaMemsetAsync(bad, 0, sizeof(int), c.st));
+  KLAUNCH_ST(h, c.st, VGICP_PROF_OTHER, k_validate_indices<<<blocks_for(nk, 256) < 1184 ? blocks_for(nk, 256) : 1184, 256, 0, c.st>>>(c.nbr.p, nk, c.n, bad));
+  CU_TRY(h, cudaGetLastError());
+  CU_TRY(h, cudaMemcpyAsync(h->map.h_counters + 8, bad, sizeof(int), cudaMemcpyDeviceToHost, c.st));
   CU_TRY(h, cudaStreamSynchronize(c.st));
+  if (h->map.h_counters[8] != 0) {
+    c.k = 0;
+    return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_neighbors: neighbour index outside [0, num_points)");
+  }
   c.k = k;
   return VGICP_OK;
 }
@@ -414,7 +432,7 @@ int voxelmap_finish(vgicp_handle h, Cloud& t, VoxelMap& m) {
   // direct-mapped index for the evaluation kernels, when the bounding box of the voxel coordinates is small enough (LiDAR scans
   // are: 84 x 84 x 10 cells for the 17k fixture, 300 x 300 x 40 at 1M points / 0.5 m); otherwise they probe the hash table
   m.dense.cells = nullptr;
-  if (h->voxel_index_mode == 0 && &m != &h->ndt_s) {
+  if (h->voxel_index_mode == 0) {
     const int* hc = m.h_counters;
     const long long nx = (long long)hc[5] - hc[2] + 1, ny = (long long)hc[6] - hc[3] + 1, nz = (long long)hc[7] - hc[4] + 1;
     if (nx > 0 && ny > 0 && nz > 0 && nx <= kDenseMaxCells && ny <= kDenseMaxCells && nz <= kDenseMaxCells && nx * ny <= kDenseMaxCells && nx * ny * nz <= kDenseMaxCells) {
@@ -526,8 +544,7 @@ LinLaunch make_lin_launch(vgicp_handle h) {
   const bool cols = h->offset_mode == 27;
   L.G = !wide ? 1 : (cols ? 3 : (n_off <= 7 ? 4 : 8));
   {
-    static int force_g = -1;
-    if (force_g < 0) { const char* e = getenv("VGICP_LIN_G"); force_g = e ? atoi(e) : 0; }
+    const int force_g = h->force_lin_g;  // VGICP_LIN_G, read once in vgicp_create (A/B measurements)
     if (cols ? (force_g == 1 || force_g == 3) : (force_g == 1 || force_g == 4 || force_g == 8)) L.G = force_g;
   }
   const int tasks_per_block = (kLinThreads / 32) * ((32 / L.G) * L.G);
@@ -627,13 +644,19 @@ int ndt_prepare(vgicp_handle h) {
   Cloud& s = h->source;
   if (!t.has_pts || !s.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "NDT: source and target clouds required");
   if (t.n <= 0 || s.n <= 0) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "NDT: empty cloud");
-  for (VoxelMap* vm : {&h->ndt_t, &h->ndt_s}) {
-    vm->created = true;
-    vm->res = (float)h->resolution;  // NDT maps are re-created with the current resolution (ndt_cuda.cu:127,138)
-  }
+  // create_{source,target}_voxelmap (ndt_cuda.cu:123-141): a map that exists is kept (with the resolution it was created with), a
+  // missing one is created with the current resolution; P2D never builds the source map
   int rc;
-  if ((rc = voxelmap_begin(h, t, h->ndt_t))) return rc;
-  if (h->problem == 2 && (rc = voxelmap_begin(h, s, h->ndt_s))) return rc;
+  if (!h->ndt_t.built && !h->ndt_t.pending) {
+    h->ndt_t.created = true;
+    h->ndt_t.res = (float)h->resolution;
+    if ((rc = voxelmap_begin(h, t, h->ndt_t))) return rc;
+  }
+  if (h->problem == 2 && !h->ndt_s.built && !h->ndt_s.pending) {
+    h->ndt_s.created = true;
+    h->ndt_s.res = (float)h->resolution;
+    if ((rc = voxelmap_begin(h, s, h->ndt_s))) return rc;
+  }
   if ((rc = voxelmap_finish(h, t, h->ndt_t))) return rc;
   if (h->problem == 2) {
     int vs = 0;
@@ -678,9 +701,10 @@ int evaluate(vgicp_handle h, const double* T, double* H36, double* b6, double* e
     }
     __sync_synchronize();
   } else {
-    CU_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * (want_H ? 43 : 1), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * (h->comm_ranks > 1 ? kLinOutCommError + 1 : (want_H ? 43 : 1)), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
   }
+  if (h->comm_ranks > 1 && h->h_out[kLinOutCommError] != 0.0) return fail(h, VGICP_ERR_COMM, "evaluate: a peer rank did not deliver its sums in time (vgicp_comm_error)");
   if (err) *err = h->h_out[0];
   if (want_H) {
     memcpy(H36, h->h_out + 1, 36 * sizeof(double));
@@ -709,9 +733,10 @@ int evaluate_spec(vgicp_handle h, const double* T, double* err_old, double* H36,
     }
     __sync_synchronize();
   } else {
-    CU_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * 44, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * (kLinOutCommError + 1), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
   }
+  if (h->comm_ranks > 1 && h->h_out[kLinOutCommError] != 0.0) return fail(h, VGICP_ERR_COMM, "evaluate: a peer rank did not deliver its sums in time (vgicp_comm_error)");
   *err_new = h->h_out[0];
   memcpy(H36, h->h_out + 1, 36 * sizeof(double));
   memcpy(b6, h->h_out + 37, 6 * sizeof(double));
@@ -735,6 +760,7 @@ int vgicp_create(int device, vgicp_handle* out) {
   vgicp_context* h = new (std::nothrow) vgicp_context();
   if (!h) return VGICP_ERR_CUDA;
   h->device = device;
+  { const char* e = getenv("VGICP_LIN_G"); h->force_lin_g = e ? atoi(e) : 0; }
   DeviceGuard g(device);
   // the kernel image is sm_100a only: fail loudly on anything else instead of falling back
   cudaFuncAttributes fa;
@@ -752,8 +778,8 @@ int vgicp_create(int device, vgicp_handle* out) {
   h->source.st = h->stream_b;  // the source's stage 1 overlaps with it
   ok = ok && cudaMalloc(&h->d_ticket, sizeof(unsigned int)) == cudaSuccess;
   for (VoxelMap* vm : {&h->map, &h->ndt_t, &h->ndt_s}) {
-    ok = ok && cudaMalloc(&vm->d_counters, 8 * sizeof(int)) == cudaSuccess;
-    ok = ok && cudaMallocHost(&vm->h_counters, 8 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMalloc(&vm->d_counters, 16 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&vm->h_counters, 16 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&vm->ev_attempt, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&vm->ev_done, cudaEventDisableTiming) == cudaSuccess;
   }
@@ -896,14 +922,21 @@ int vgicp_set_target_cloud(vgicp_handle h, const float* xyz, size_t n, size_t st
 int vgicp_swap_source_and_target(vgicp_handle h) {  // fast_vgicp_cuda.cu:97-107
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
-  // the clouds keep their streams; everything in flight (incl. a pending map build that reads the old target) must land first
+  // whole Cloud records are swapped, streams and `ready` events included (sync_inputs compares each cloud's stream with the main
+  // stream, so it does not matter which one ends up where); everything in flight (incl. a pending map build that reads the old
+  // target) must land first
   if (h->map.pending) { int rc0 = voxelmap_finish(h, h->target, h->map); if (rc0) return rc0; }
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream_b));
   std::swap(h->source, h->target);
   h->map.built = false;
   h->map.pending = false;
-  h->ndt_ready = false;  // NDT: the reference swaps its two maps (ndt_cuda.cu:93-96); here they are rebuilt on demand
+  // NDT: the reference swaps its two maps (ndt_cuda.cu:90-93); a map that does not exist (P2D never builds the source's) is built by
+  // the next create_voxelmaps.  Pending builds were enqueued on the old streams: both streams are idle here.
+  for (VoxelMap* vm : {&h->ndt_t, &h->ndt_s})
+    if (vm->pending) { vm->pending = false; vm->built = false; }
+  std::swap(h->ndt_t, h->ndt_s);
+  h->ndt_ready = false;
   if (h->problem != 0) return VGICP_OK;
   if (!h->target.has_pts || !h->target.has_cov) return VGICP_OK;
   return build_voxelmap(h);
@@ -1281,12 +1314,14 @@ int vgicp_register(vgicp_handle h, const float* target_xyz, size_t n_target, con
   h->target.k = 0; h->target.has_cov = false; h->map.built = false; h->map.pending = false;
   if ((rc = set_cloud(h, h->target, target_xyz, n_target, stride_bytes, on_device != 0))) return rc;
   if ((rc = find_neighbors(h, h->target, k))) return rc;
-  if ((rc = calc_covariances(h, h->target, regularization_method))) return rc;
+  // NORMALIZED_MIN_EIG: raw covariances kept and VGICP_ERR_UNSUPPORTED reported (the reference prints a message and carries on,
+  // covariance_regularization.cu:121-123); the class wrappers tolerate that code, so does the one-call registration
+  if ((rc = calc_covariances(h, h->target, regularization_method)) && rc != VGICP_ERR_UNSUPPORTED) return rc;
   if ((rc = build_voxelmap(h))) return rc;
   h->source.k = 0; h->source.has_cov = false;
   if ((rc = set_cloud(h, h->source, source_xyz, n_source, stride_bytes, on_device != 0))) return rc;
   if ((rc = find_neighbors(h, h->source, k))) return rc;
-  if ((rc = calc_covariances(h, h->source, regularization_method))) return rc;
+  if ((rc = calc_covariances(h, h->source, regularization_method)) && rc != VGICP_ERR_UNSUPPORTED) return rc;
   double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   return vgicp_align(h, guess ? guess : I, params, result);
 }
@@ -1361,6 +1396,11 @@ int vgicp_comm_init(vgicp_handle h, int rank, int nranks, const unsigned char* a
   h->comm_rank = rank;
   h->comm_ranks = nranks;
   h->comm_seq = 0;
+  // the mailbox outlives vgicp_comm_shutdown: flags left by a previous session could equal the first tags of this one.  Clear it
+  // here; the caller puts a host barrier between vgicp_comm_init on all ranks and the first evaluation (see the header), so no
+  // peer writes into it before the clear has landed.
+  CU_TRY(h, cudaMemsetAsync(h->comm_box, 0, sizeof(CommMailbox), h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
   return VGICP_OK;
 }
 
@@ -1417,8 +1457,7 @@ int vgicp_ndt_create_voxelmaps(vgicp_handle h) {  // NDTCudaCore::create_voxelma
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
   if (h->problem == 0) return fail(h, VGICP_ERR_BAD_STATE, "ndt_create_voxelmaps: select an NDT problem first (vgicp_set_problem)");
-  h->ndt_ready = false;
-  return ndt_prepare(h);
+  return ndt_prepare(h);  // idempotent like the reference's: existing maps are kept
 }
 
 int vgicp_set_execution_hint(vgicp_handle h, int hint) {

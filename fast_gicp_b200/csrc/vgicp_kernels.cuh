@@ -29,6 +29,7 @@ constexpr int kLinThreads = 128;     // block size of the linearize kernel
 constexpr int kLinMaxBlocks = 592;   // 4 x 148 SMs: upper bound on partial sums the last block has to fold (more resident warps only thrash L1: measured)
 constexpr int kLinValues = 28;       // 21 unique H + 6 b + 1 err
 constexpr int kLinStride = 32;       // row length of the partial-sum arrays (the speculative evaluation carries 29 values)
+constexpr int kLinOutCommError = 44; // out[44]: 1.0 when a sharded evaluation timed out waiting for a peer (the sums are then incomplete)
 
 struct Pose {      // float image of an Eigen::Isometry3f: R row-major here, t
   float r[9];
@@ -135,6 +136,13 @@ __device__ __forceinline__ int dense_offset(const DenseIndex& d, int x, int y, i
 __global__ void k_fill_i32(int* __restrict__ p, int v, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+}
+
+// set_{source,target}_neighbors: flag any caller-supplied neighbour index outside [0, n)
+__global__ void k_validate_indices(const int* __restrict__ idx, size_t count, int n, int* __restrict__ bad) {
+  bool any = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) any |= (unsigned)idx[i] >= (unsigned)n;
+  if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(bad, 1);
 }
 
 __device__ __forceinline__ bool coord_eq(int4 a, int4 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
@@ -724,6 +732,7 @@ __device__ __forceinline__ bool lin_reduce(const LinArgs& a, const float* sum, d
       for (int q = 0; q < a.comm_ranks; q++) s += *reinterpret_cast<const volatile double*>(&me->vals[half][q][threadIdx.x]);
       fin[0][threadIdx.x] = s;
     }
+    if (threadIdx.x == 0) a.out[kLinOutCommError] = (double)a.comm_peers[a.comm_rank]->error;  // sticky; the host turns it into VGICP_ERR_COMM
     __syncthreads();
   }
   return true;

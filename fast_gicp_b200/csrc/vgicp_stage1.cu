@@ -258,6 +258,10 @@ __global__ void __launch_bounds__(128) k_covariance_knn(const float4* __restrict
 // blocks of 512 like the reference's per-block async transforms; partial sums per 512-block are folded in block order
 // (the reference's strided finalisation, :92-114).  The reference pads the cloud to a multiple of 512 with points at the
 // origin (:126-129) which pick up weight whenever the query is within max_dist of the origin -- reproduced.
+// All nine entries of sum w p p^T are kept ((w p_r) p_c and (w p_c) p_r round differently and the reference's Matrix3f holds
+// both).  The weight is exp evaluated in double and rounded once: the reference calls CUDA's 2-ulp expf, which no CPU checker can
+// reproduce bit for bit; the correctly rounded value lies within that function's own error bound and makes the stage testable
+// bit-for-bit like the rest of this file.
 __global__ void __launch_bounds__(128) k_covariance_rbf(const float4* __restrict__ pts, int n, float exp_factor, float max_dist, int method, float4* __restrict__ covA,
                                                        float2* __restrict__ covB) {
   __shared__ float4 tile[kRbfBlock];
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(128) k_covariance_rbf(const float4* __restrict
   const bool active = q < n;
   float4 x = active ? pts[q] : make_float4(0.f, 0.f, 0.f, 0.f);
   const float max_dist_sq = max_dist * max_dist;
-  float sw = 0.f, m[3] = {0.f, 0.f, 0.f}, c[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float sw = 0.f, m[3] = {0.f, 0.f, 0.f}, c[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // c: row-major
   const int nblocks = (n + kRbfBlock - 1) / kRbfBlock;
   for (int b = 0; b < nblocks; b++) {
     __syncthreads();
@@ -276,31 +280,34 @@ __global__ void __launch_bounds__(128) k_covariance_rbf(const float4* __restrict
     }
     __syncthreads();
     if (!active) continue;
-    float psw = 0.f, pm[3] = {0.f, 0.f, 0.f}, pc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float psw = 0.f, pm[3] = {0.f, 0.f, 0.f}, pc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < kRbfBlock; j++) {
       float4 p = tile[j];
       float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
       float sq = (dx * dx + dy * dy) + dz * dz;
       if (sq > max_dist_sq) continue;
-      float w = expf(-exp_factor * sq);
+      float w = (float)exp((double)(-exp_factor * sq));
       psw += w;
       float wx = w * p.x, wy = w * p.y, wz = w * p.z;
       pm[0] += wx; pm[1] += wy; pm[2] += wz;
-      pc[0] += wx * p.x; pc[1] += wx * p.y; pc[2] += wx * p.z; pc[3] += wy * p.y; pc[4] += wy * p.z; pc[5] += wz * p.z;
+      pc[0] += wx * p.x; pc[1] += wx * p.y; pc[2] += wx * p.z;
+      pc[3] += wy * p.x; pc[4] += wy * p.y; pc[5] += wy * p.z;
+      pc[6] += wz * p.x; pc[7] += wz * p.y; pc[8] += wz * p.z;
     }
     sw += psw;
 #pragma unroll
     for (int d = 0; d < 3; d++) m[d] += pm[d];
 #pragma unroll
-    for (int d = 0; d < 6; d++) c[d] += pc[d];
+    for (int d = 0; d < 9; d++) c[d] += pc[d];
   }
   if (!active) return;
   // NormalDistribution::finalize :47-53:  mean = sum/sw ; cov = (cov - mean*sum^T)/sw
   float mean[3] = {m[0] / sw, m[1] / sw, m[2] / sw};
   float cc[9];
-  cc[0] = (c[0] - mean[0] * m[0]) / sw; cc[1] = (c[1] - mean[0] * m[1]) / sw; cc[2] = (c[2] - mean[0] * m[2]) / sw;
-  cc[3] = (c[1] - mean[1] * m[0]) / sw; cc[4] = (c[3] - mean[1] * m[1]) / sw; cc[5] = (c[4] - mean[1] * m[2]) / sw;
-  cc[6] = (c[2] - mean[2] * m[0]) / sw; cc[7] = (c[4] - mean[2] * m[1]) / sw; cc[8] = (c[5] - mean[2] * m[2]) / sw;
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int col = 0; col < 3; col++) cc[r * 3 + col] = (c[r * 3 + col] - mean[r] * m[col]) / sw;
   regularize_cov(cc, method);
   store_cov_sym(cc, covA, covB, q);
 }
@@ -912,12 +919,9 @@ cudaError_t launch_regularize_voxels(VoxelRec* vox, const int* nv_ptr, int vmax,
 size_t knn_smem_bytes(int k) { return sizeof(float4) * kKnnTile + (size_t)k * kKnnThreads * (sizeof(float) + sizeof(int)); }
 
 cudaError_t launch_knn_bruteforce(const float4* pts, int n, int k, int* nbr, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_knn_bruteforce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(kMaxK));
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  // per device and thread-safe: set on every call (a host-side attribute write; this engine is the A/B legacy path)
+  cudaError_t e = cudaFuncSetAttribute(k_knn_bruteforce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)knn_smem_bytes(kMaxK));
+  if (e != cudaSuccess) return e;
   k_knn_bruteforce<<<(n + kKnnThreads - 1) / kKnnThreads, kKnnThreads, knn_smem_bytes(k), stream>>>(pts, n, k, nbr);
   return cudaGetLastError();
 }

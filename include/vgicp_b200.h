@@ -163,7 +163,9 @@ VGICP_API int vgicp_set_target_cloud_device(vgicp_handle h, const float* d_xyz, 
  * (vgicp_set_source_shard); the last block of each evaluation kernel stores its 28 folded sums into every peer's mailbox over
  * NVLink peer memory, waits for the peers' sums and adds them in rank order, so vgicp_compute_error / vgicp_align return the
  * same H, b, err on every rank.  Setup: each rank calls vgicp_comm_export, the 64-byte handles are all-gathered by any host
- * transport (torch.distributed, MPI, files), then vgicp_comm_init.  Ranks must issue the same sequence of evaluations. */
+ * transport (torch.distributed, MPI, files), then vgicp_comm_init (which clears this rank's mailbox), then a host barrier over all
+ * ranks before the first evaluation.  Ranks must issue the same sequence of evaluations.  An evaluation whose wait for a peer times
+ * out returns VGICP_ERR_COMM (the sums are incomplete); vgicp_comm_error reads the sticky flag. */
 VGICP_API int vgicp_comm_export(vgicp_handle h, unsigned char* handle64);
 VGICP_API int vgicp_comm_init(vgicp_handle h, int rank, int nranks, const unsigned char* all_handles /* nranks x 64 bytes */);
 VGICP_API int vgicp_comm_shutdown(vgicp_handle h);
@@ -174,7 +176,9 @@ VGICP_API int vgicp_clear_source_shard(vgicp_handle h);
  * The same handle solves the NDT problems: vgicp_set_problem selects VGICP (0, default), NDT point-to-distribution (1) or NDT
  * distribution-to-distribution (2; NDTDistanceMode order P2D, D2D of ndt_settings.hpp:6, plus one).  With an NDT problem selected
  *   set_{source,target}_cloud, set_resolution, set_neighbor_search_method, swap_source_and_target   as NDTCudaCore's members (:36-48)
- *   vgicp_ndt_create_voxelmaps      NDTCudaCore::create_voxelmaps (ndt_cuda.cu:118-141): points-only voxel Gaussians + MIN_EIG
+ *   vgicp_ndt_create_voxelmaps      NDTCudaCore::create_voxelmaps (ndt_cuda.cu:118-141): points-only voxel Gaussians + MIN_EIG; a map
+ *                                   that exists is kept with the resolution it was built with (set_*_cloud resets that cloud's map,
+ *                                   swap_source_and_target swaps the two maps), exactly as the reference's early returns (:125,136)
  *   vgicp_update_correspondences    NDTCudaCore::update_correspondences (:143-162): source points (P2D) or source voxel means (D2D)
  *   vgicp_compute_error / vgicp_align   NDTCudaCore::compute_error (:164-177) -> {p2d,d2d}_ndt_compute_derivatives
  *   vgicp_get_voxel_* / vgicp_get_num_voxels / vgicp_get_voxel_buckets   read the NDT target map

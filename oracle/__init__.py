@@ -66,6 +66,7 @@ def lib():
         L.orc_knn_bruteforce.argtypes = [fp, C.c_int, C.c_int, ip, fp]
         L.orc_knn_kdtree.argtypes = [fp, C.c_int, C.c_int, ip]
         L.orc_covariances.argtypes = [fp, C.c_int, C.c_int, ip, fp]
+        L.orc_covariances_rbf.argtypes = [fp, C.c_int, C.c_float, C.c_float, fp]
         L.orc_eig3_direct.argtypes = [fp, fp, fp]
         L.orc_regularize.argtypes = [fp, C.c_int, C.c_int]
         L.orc_voxelmap_build.restype = vp
@@ -173,6 +174,14 @@ def covariances(pts, nbr):
     return out
 
 
+def covariances_rbf(pts, kernel_width=0.5, max_dist=3.0):
+    """covariance_estimation_rbf.cu:59-151 (NearestNeighborMethod::GPU_RBF_KERNEL); defaults = fast_vgicp_cuda_impl.hpp:31."""
+    pts = _f32(pts)
+    out = np.empty((len(pts), 9), dtype=np.float32)
+    lib().orc_covariances_rbf(_p(pts, C.c_float), len(pts), C.c_float(kernel_width), C.c_float(max_dist), _p(out, C.c_float))
+    return out
+
+
 def eig3_direct(cov9):
     cov9 = _f32(cov9).reshape(9)
     ev = np.empty(3, dtype=np.float32)
@@ -187,7 +196,9 @@ def regularize(cov9, method=REG_PLANE):
     return out
 
 
-def estimate_covariances(pts, k=20, method=REG_PLANE, knn_method="kdtree"):
+def estimate_covariances(pts, k=20, method=REG_PLANE, knn_method="kdtree", kernel_width=0.5, max_dist=3.0):
+    if knn_method == "rbf":  # calculate_*_covariances_rbf (fast_vgicp_cuda.cu:205-219): RBF-weighted covariance + the same regulariser
+        return regularize(covariances_rbf(pts, kernel_width, max_dist), method)
     nbr = knn(pts, k, knn_method)
     return regularize(covariances(pts, nbr), method)
 
@@ -323,10 +334,21 @@ def register_ndt(target, source, res=1.0, mode=D2D, method=DIRECT7, radius=-1.0,
     return AlignResult(r)
 
 
-def register_f32(target, source, k=20, reg=REG_PLANE, res=1.0, method=DIRECT1, radius=-1.0, guess=None, params=None, knn_method="kdtree", accum_double=False):
-    """Whole FastVGICPCuda registration (setInputTarget + setInputSource + align) with the float oracle."""
-    tc = estimate_covariances(target, k, reg, knn_method)
-    sc = estimate_covariances(source, k, reg, knn_method)
+def symmetrized(cov9):
+    """(C + C^T)/2 in float: the packed 24-byte covariance the CUDA path stores (V L V^-1 is symmetric only up to rounding)."""
+    m = _f32(cov9).reshape(-1, 3, 3)
+    return (np.float32(0.5) * (m + m.transpose(0, 2, 1))).reshape(-1, 9)
+
+
+def register_f32(target, source, k=20, reg=REG_PLANE, res=1.0, method=DIRECT1, radius=-1.0, guess=None, params=None, knn_method="kdtree", accum_double=False,
+                 kernel_width=0.5, max_dist=3.0, symmetrize=False):
+    """Whole FastVGICPCuda registration (setInputTarget + setInputSource + align) with the float oracle.  knn_method "rbf" =
+    NearestNeighborMethod::GPU_RBF_KERNEL; symmetrize=True feeds the symmetric part of the regularised covariances (what the CUDA
+    path stores)."""
+    tc = estimate_covariances(target, k, reg, knn_method, kernel_width, max_dist)
+    sc = estimate_covariances(source, k, reg, knn_method, kernel_width, max_dist)
+    if symmetrize:
+        tc, sc = symmetrized(tc), symmetrized(sc)
     vm = VoxelMap(target, tc, res, accum_double=accum_double)
     return align_f32(vm, source, sc, offsets(method, radius), guess, params)
 

@@ -256,6 +256,54 @@ ORC_API void orc_covariances(const float* pts, int n, int k, const int* nbr, flo
 }
 
 /* ------------------------------------------------------------------------------------------------------------
+ * (3b) kernel-weighted covariance estimation (NearestNeighborMethod::GPU_RBF_KERNEL)  --  covariance_estimation_rbf.cu
+ *     covariance_estimation_kernel :59-90 : for each block of BLOCK_SIZE = 512 consecutive points (the cloud is padded to a
+ *       multiple of 512 with points at the origin, :126-129) and each query x: a NormalDistribution partial
+ *       {sum_w, sum w*p, sum w*p*p^T} over the block's points with |x - p|^2 <= max_dist^2, w = exp(-kernel_width * |x - p|^2),
+ *       accumulated in index order (NormalDistribution::accumulate :40-44);
+ *     finalization_kernel :92-114 : the partials of a query are added in block order (operator+= :33-38), then
+ *       NormalDistribution::finalize :46-52 : mean = sum_p / sum_w ; cov = (cov - mean * sum_p^T) / sum_w   (not symmetrised).
+ *     A padding point inside max_dist of the query adds its weight to sum_w (and nothing else, it sits at the origin).
+ *     float throughout, every a*b+c two roundings (the CUDA path's stage-1 unit is compiled --fmad=false and spells the same
+ *     sequence).  The weight: the reference calls CUDA's expf (a 2-ulp function that no CPU libm reproduces bit for bit); both
+ *     sides here evaluate exp in double and round once, i.e. the correctly rounded float -- within the error bound of the
+ *     reference's own function.  cov9: column-major 3x3 per point like every other covariance of the oracle.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define ORC_RBF_BLOCK 512
+ORC_API void orc_covariances_rbf(const float* pts, int n, float kernel_width, float max_dist, float* cov9) {
+  const float max_dist_sq = max_dist * max_dist;
+  const int num_blocks = (n + ORC_RBF_BLOCK - 1) / ORC_RBF_BLOCK;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int q = 0; q < n; q++) {
+    const float* x = pts + 3 * (size_t)q;
+    float sw = 0.f, m[3] = {0.f, 0.f, 0.f}, c[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b = 0; b < num_blocks; b++) {
+      float psw = 0.f, pm[3] = {0.f, 0.f, 0.f}, pc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < ORC_RBF_BLOCK; j++) {
+        const int g = b * ORC_RBF_BLOCK + j;
+        static const float origin[3] = {0.f, 0.f, 0.f};
+        const float* p = g < n ? pts + 3 * (size_t)g : origin;
+        const float dx = x[0] - p[0], dy = x[1] - p[1], dz = x[2] - p[2];
+        const float sq = (dx * dx + dy * dy) + dz * dz;
+        if (sq > max_dist_sq) continue;
+        const float w = (float)exp((double)(-kernel_width * sq));
+        psw += w;
+        const float wp[3] = {w * p[0], w * p[1], w * p[2]};
+        for (int d = 0; d < 3; d++) pm[d] += wp[d];
+        for (int col = 0; col < 3; col++)
+          for (int row = 0; row < 3; row++) pc[col * 3 + row] += wp[row] * p[col];
+      }
+      sw += psw;
+      for (int d = 0; d < 3; d++) m[d] += pm[d];
+      for (int d = 0; d < 9; d++) c[d] += pc[d];
+    }
+    const float mean[3] = {m[0] / sw, m[1] / sw, m[2] / sw};
+    for (int col = 0; col < 3; col++)
+      for (int row = 0; row < 3; row++) cov9[(size_t)q * 9 + col * 3 + row] = (c[col * 3 + row] - mean[row] * m[col]) / sw;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
  * (4) covariance regularisation  --  covariance_regularization.cu:15-25,34-52,74-101,105-124
  * ---------------------------------------------------------------------------------------------------------- */
 /* column-major 3x3 helpers: M(r,c) = m[c*3+r] */

@@ -1,9 +1,7 @@
 """Batch registration (include/vgicp_batch_b200.h): a pool of handles + worker threads over the public C ABI; every pair is one
 vgicp_register on one handle, so the results must equal the sequential loop's bit for bit whatever the interleaving.
 
-CPU: the library loads and exports exactly what its header declares.  GPU: batch vs sequential, in a child process and
-expected-to-fail-tolerant (the library was written after the round-1 GPU budget was spent and has not run on hardware yet;
-round 2 makes it a hard test and moves bench.py's end-to-end arm onto it)."""
+CPU: the library loads and exports exactly what its header declares.  GPU: batch vs sequential, in a child process."""
 import os
 import re
 import subprocess
@@ -62,7 +60,6 @@ print("batch ok")
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="batch library not yet run on hardware (written after the round-1 GPU budget was spent)")
 def test_gpu_batch_equals_the_sequential_loop():
     code = _CHILD % (ROOT, os.path.join(ROOT, "tests", "golden", "pair_0p2.npz"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)

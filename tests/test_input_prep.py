@@ -3,9 +3,8 @@
 CPU part: the oracle restatement against the reference's goldens and against the numpy restatement that made the fixtures; the
 parallel formulation the CUDA kernels implement (512 independent history chains, flushed centroids ranked by the index of the
 flushing point) against the serial filter; the C ABI surface of lib/libvgicp_prep_b200.so.
-GPU part (-m gpu): the CUDA library against the oracle, bit for bit.  It has not run on hardware yet (the round-1 GPU budget
-was spent before it was written), so it is expected-to-fail-tolerant (xfail, non-strict) and runs in a child process: a fault
-there cannot poison the CUDA context of the other GPU tests.  Round 2 turns it into a hard test."""
+GPU part (-m gpu): the CUDA library against the oracle, bit for bit (in a child process: a fault there cannot poison the CUDA
+context of the other GPU tests)."""
 import os
 import subprocess
 import sys
@@ -191,7 +190,6 @@ print("prep ok")
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="CUDA input-prep kernels not yet run on hardware (written after the round-1 GPU budget was spent)")
 def test_gpu_input_prep_matches_the_oracle_bit_for_bit():
     code = _CHILD % (ROOT, os.path.join(ROOT, "tests"), os.path.join(GOLDEN, "pair_0p2.npz"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)

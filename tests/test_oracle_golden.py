@@ -179,3 +179,33 @@ def test_oracle_ndt_voxel_covariances_min_eig(pair02):
     P = tgt[sel].astype(np.float64)
     want = np.cov(P.T, bias=True)
     assert np.abs(vm.vox_cov[v].reshape(3, 3) - want).max() < 1e-3
+
+
+def test_rbf_covariances_against_direct_evaluation(pair02, relative_pose):
+    """covariance_estimation_rbf.cu:59-151 restated (orc_covariances_rbf): against the defining formula evaluated directly in
+    double -- kernel-weighted mean/covariance over the points within max_dist, with the reference's quirk that the cloud is padded
+    to a multiple of 512 with points at the origin (:126-129) which add to the weight sum of queries near the origin -- and end to
+    end: a registration with RBF covariances meets the reference's gate against data/relative.txt."""
+    rng = np.random.default_rng(2)
+    pts = (rng.normal(size=(1500, 3)) * [3.0, 3.0, 0.2]).astype(np.float32)
+    kw, md = 0.5, 3.0
+    got = O.covariances_rbf(pts, kw, md).reshape(-1, 3, 3).transpose(0, 2, 1)  # column-major image -> [row, col]
+    P = pts.astype(np.float64)
+    npad = (-len(P)) % 512
+    assert npad > 0
+    ext = np.vstack([P, np.zeros((npad, 3))])
+    near_origin = 0
+    for i in range(0, len(P), 37):
+        d2 = ((ext - P[i]) ** 2).sum(axis=1)
+        w = np.where(d2 <= md * md, np.exp(-kw * d2), 0.0)
+        near_origin += int(w[len(P):].sum() > 0)
+        sw = w.sum()
+        s1 = (w[:, None] * ext).sum(axis=0)
+        s2 = (w[:, None, None] * ext[:, :, None] * ext[:, None, :]).sum(axis=0)
+        want = (s2 - np.outer(s1 / sw, s1)) / sw
+        assert np.abs(got[i] - want).max() < 2e-5 * max(1.0, np.abs(want).max()), i
+    assert near_origin > 0  # the padding quirk is exercised
+    tgt, src = pair02
+    r = O.register_f32(tgt, src, method=O.DIRECT1, knn_method="rbf")
+    dt, dr = pose_error(relative_pose, r.T)
+    assert r.converged and dt < T_TOL and dr < R_TOL, (dt, dr)
