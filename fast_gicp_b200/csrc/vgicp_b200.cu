@@ -89,9 +89,15 @@ struct VoxelMap {
   DevBuf<int4> coords;
   DevBuf<int> slots;
   DevBuf<int> slot_of_point;
-  DevBuf<double> sums;
-  DevBuf<int> counts;
-  void release() { buckets.release(); vox.release(); coords.release(); slots.release(); slot_of_point.release(); sums.release(); counts.release(); dense_cells.release(); chunk_state.release(); }
+  // points stably sorted by voxel id for the ordered per-voxel sums (vgicp_sort.cuh)
+  DevBuf<unsigned> sort_keys[2], sort_vals[2];
+  DevBuf<unsigned char> sort_scratch;
+  DevBuf<int2> segments;
+  void release() {
+    buckets.release(); vox.release(); coords.release(); slots.release(); slot_of_point.release(); dense_cells.release(); chunk_state.release();
+    for (int j = 0; j < 2; j++) { sort_keys[j].release(); sort_vals[j].release(); }
+    sort_scratch.release(); segments.release();
+  }
 };
 
 }  // namespace
@@ -294,7 +300,7 @@ int find_neighbors(vgicp_handle h, Cloud& c, int k) {
     CU_TRY(h, c.knn_scratch.reserve(need));
     int nl = 0;
     KLAUNCH_ST(h, c.st, VGICP_PROF_KNN,
-            ke = launch_knn_grid(c.pts.p, c.n, k, c.nbr.p, c.knn_scratch.p, c.knn_scratch.cap, (h->knn_mode == 1 || c.n < 256) ? 1 : 0, h->exec_hint == 1 ? 2 : 4, &nl, c.st));
+            ke = launch_knn_grid(c.pts.p, c.n, k, c.nbr.p, c.knn_scratch.p, c.knn_scratch.cap, (h->knn_mode == 1 || c.n < 256) ? 1 : 0, 0, c.n, &nl, c.st));
     h->launches += nl > 0 ? nl - 1 : 0;
   }
   CU_TRY(h, ke);
@@ -327,7 +333,11 @@ int calc_covariances_rbf(vgicp_handle h, Cloud& c, int method) {
   CU_TRY(h, c.covB.reserve(c.n));
   if (c.n > 0) {
     cudaError_t ke = cudaSuccess;
-    KLAUNCH_ST(h, c.st, VGICP_PROF_COVARIANCE, ke = launch_covariance_rbf(c.pts.p, c.n, (float)h->kernel_width, (float)h->kernel_max_dist, method, c.covA.p, c.covB.p, c.st));
+    const size_t box_bytes = sizeof(float) * 6 * (size_t)((c.n + kRbfBlock - 1) / kRbfBlock);
+    CU_TRY(h, c.knn_scratch.reserve(box_bytes));  // (the k-NN scratch is idle here: RBF covariances use no neighbour table)
+    KLAUNCH_ST(h, c.st, VGICP_PROF_COVARIANCE,
+               ke = launch_covariance_rbf(c.pts.p, c.n, (float)h->kernel_width, (float)h->kernel_max_dist, method, reinterpret_cast<float*>(c.knn_scratch.p), c.covA.p, c.covB.p, c.st));
+    h->launches++;
     CU_TRY(h, ke);
   }
   c.has_cov = true;
@@ -427,8 +437,6 @@ int voxelmap_finish(vgicp_handle h, Cloud& t, VoxelMap& m) {
   if (vmax > (1 << 27)) { m.pending = false; return fail(h, VGICP_ERR_INVALID_ARGUMENT, "create_target_voxelmap: more than 2^27 voxels (the evaluation kernels pack a voxel id in 27 bits)"); }
   CU_TRY(h, m.buckets.reserve(B));
   CU_TRY(h, m.vox.reserve(vmax));
-  CU_TRY(h, m.sums.reserve((size_t)vmax * 10));
-  CU_TRY(h, m.counts.reserve(vmax));
   // direct-mapped index for the evaluation kernels, when the bounding box of the voxel coordinates is small enough (LiDAR scans
   // are: 84 x 84 x 10 cells for the 17k fixture, 300 x 300 x 40 at 1M points / 0.5 m); otherwise they probe the hash table
   m.dense.cells = nullptr;
@@ -457,18 +465,41 @@ int voxelmap_finish(vgicp_handle h, Cloud& t, VoxelMap& m) {
     KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP,
                k_table_assign_ids<<<chunks, 1024, 0, t.st>>>(m.coords.p, m.slots.p, B, m.buckets.p, m.d_counters + 1, m.dense, m.chunk_state.p, m.chunk_epoch));
   }
-  CU_TRY(h, cudaMemsetAsync(m.sums.p, 0, sizeof(double) * 10 * (size_t)vmax, t.st));
-  CU_TRY(h, cudaMemsetAsync(m.counts.p, 0, sizeof(int) * (size_t)vmax, t.st));
-  if (m.ndt) {
-    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_accumulate_ndt<<<blocks_for(n, 256), 256, 0, t.st>>>(t.pts.p, n, m.slot_of_point.p, m.buckets.p, m.sums.p, m.counts.p));
-    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_finalize_ndt<<<blocks_for(vmax, 256), 256, 0, t.st>>>(m.sums.p, m.counts.p, m.d_counters + 1, m.vox.p));
-    cudaError_t ke = cudaSuccess;
-    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, ke = launch_regularize_voxels(m.vox.p, m.d_counters + 1, vmax, VGICP_REG_MIN_EIG, t.st));  // ndt_cuda.cu:129,140
-    CU_TRY(h, ke);
-  } else {
+  // voxel Gaussians: stable sort of the points by voxel id, then one warp per voxel adds its points in index order
+  {
+    int key_bits = 1;
+    while ((1 << key_bits) < B) key_bits++;
+    key_bits += 1;  // ids < B; the all-ones key marks the points of dropped voxels (sorts last)
+    const unsigned invalid = (1u << key_bits) - 1u;
+    const int passes = sort_num_passes(key_bits);
+    const size_t sbytes = sort_scratch_bytes(n, passes);
+    for (int j = 0; j < 2; j++) {
+      CU_TRY(h, m.sort_keys[j].reserve(n));
+      CU_TRY(h, m.sort_vals[j].reserve(n));
+    }
+    CU_TRY(h, m.sort_scratch.reserve(sbytes));
+    CU_TRY(h, m.segments.reserve(vmax));
+    CU_TRY(h, cudaMemsetAsync(m.sort_scratch.p, 0, sbytes, t.st));
+    const int kb = blocks_for(n, kSortThreads);
     KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP,
-               k_voxel_accumulate<<<blocks_for(n, 256), 256, 0, t.st>>>(t.pts.p, t.covA.p, t.covB.p, n, m.slot_of_point.p, m.buckets.p, m.sums.p, m.counts.p));
-    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_finalize<<<blocks_for(vmax, 256), 256, 0, t.st>>>(m.sums.p, m.counts.p, m.d_counters + 1, m.vox.p));
+               k_voxel_sort_keys<<<kb < 1184 ? kb : 1184, kSortThreads, 0, t.st>>>(m.slot_of_point.p, m.buckets.p, n, invalid, passes, m.sort_keys[0].p, reinterpret_cast<unsigned*>(m.sort_scratch.p)));
+    int nl = 0;
+    cudaError_t se = cudaSuccess;
+    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP,
+               se = launch_sort_pairs<unsigned>(m.sort_keys[0].p, m.sort_vals[0].p, m.sort_keys[1].p, m.sort_vals[1].p, n, key_bits, m.sort_scratch.p, true, nullptr, nullptr, &nl, t.st));
+    CU_TRY(h, se);
+    h->launches += nl > 0 ? nl - 1 : 0;
+    const unsigned* skeys = m.sort_keys[passes & 1].p;
+    const unsigned* order = m.sort_vals[passes & 1].p;
+    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_segments<<<blocks_for(n, 256), 256, 0, t.st>>>(skeys, n, invalid, m.segments.p));
+    if (m.ndt) {
+      KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_reduce<true><<<blocks_for(vmax, 4), 128, 0, t.st>>>(t.pts.p, nullptr, nullptr, order, m.segments.p, m.d_counters + 1, m.vox.p));
+      cudaError_t ke = cudaSuccess;
+      KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, ke = launch_regularize_voxels(m.vox.p, m.d_counters + 1, vmax, VGICP_REG_MIN_EIG, t.st));  // ndt_cuda.cu:129,140
+      CU_TRY(h, ke);
+    } else {
+      KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_reduce<false><<<blocks_for(vmax, 4), 128, 0, t.st>>>(t.pts.p, t.covA.p, t.covB.p, order, m.segments.p, m.d_counters + 1, m.vox.p));
+    }
   }
   CU_TRY(h, cudaGetLastError());
   CU_TRY(h, cudaMemcpyAsync(m.h_counters + 1, m.d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, t.st));

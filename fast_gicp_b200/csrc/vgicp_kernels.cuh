@@ -21,6 +21,7 @@
 #include <stdint.h>
 
 #include "lsq_math.hpp"
+#include "vgicp_sort.cuh"
 #include "vgicp_stage1.cuh"
 
 namespace vgicp {
@@ -260,69 +261,97 @@ __global__ void __launch_bounds__(1024) k_table_assign_ids(const int4* __restric
   }
 }
 
-// accumulate_points_kernel :76-120 with double accumulators (the reference uses float atomicAdd in arrival order;
-// double sums rounded once make the result independent of the order to float precision).  sums: [V][10] doubles
-// (mean 3, cov 6 packed, spare), counts: [V].
-__global__ void k_voxel_accumulate(const float4* __restrict__ pts, const float4* __restrict__ covA, const float2* __restrict__ covB, int n, const int* __restrict__ slot_of_point,
-                                   const int4* __restrict__ buckets, double* __restrict__ sums, int* __restrict__ counts) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int s = slot_of_point[i];
-  if (s < 0) return;
-  int id = buckets[s].w;
-  float4 p = pts[i];
-  float4 a = covA[i];
-  float2 b = covB[i];
-  double* d = sums + (size_t)id * 10;
-  atomicAdd(&counts[id], 1);
-  atomicAdd(d + 0, (double)p.x); atomicAdd(d + 1, (double)p.y); atomicAdd(d + 2, (double)p.z);
-  atomicAdd(d + 3, (double)a.x); atomicAdd(d + 4, (double)a.y); atomicAdd(d + 5, (double)a.z);
-  atomicAdd(d + 6, (double)a.w); atomicAdd(d + 7, (double)b.x); atomicAdd(d + 8, (double)b.y);
+// Voxel Gaussians: accumulate_points_kernel :76-120 + finalize_voxels_kernel :158-176 (VGICP: per-point covariances) and
+// accumulate / ndt_finalize_voxels_kernel :122-148,178-198 (NDT: the points alone).  The reference adds floats with atomicAdd in
+// arrival order (thread-timing dependent).  Here the points are stably sorted by voxel id (vgicp_sort.cuh: index ascending inside
+// a voxel), and one warp per voxel adds its points IN POINT ORDER in double, each of ten lanes one component, and rounds once:
+// exactly the sums of the CPU checker, bit for bit, and no atomics (hot voxels hold thousands of points at 1 M points).
+// k_voxel_sort_keys: sort key of point i = its voxel id, or `invalid` (sorts last) for the points of dropped voxels; also counts
+// the sort's digits.
+__global__ void __launch_bounds__(kSortThreads) k_voxel_sort_keys(const int* __restrict__ slot_of_point, const int4* __restrict__ buckets, int n, unsigned invalid, int passes,
+                                                                  unsigned* __restrict__ keys, unsigned* __restrict__ hist) {
+  __shared__ unsigned sh[kSortMaxPasses * kSortBins];
+  for (int i = threadIdx.x; i < passes * kSortBins; i += kSortThreads) sh[i] = 0;
+  __syncthreads();
+  const int n_round = (n + 31) & ~31;
+  for (int i = blockIdx.x * kSortThreads + threadIdx.x; i < n_round; i += gridDim.x * kSortThreads) {
+    const bool valid = i < n;
+    unsigned key = invalid;
+    if (valid) {
+      const int s = slot_of_point[i];
+      if (s >= 0) key = (unsigned)buckets[s].w;
+      keys[i] = key;
+    }
+    sort_hist_add(sh, passes, valid, (unsigned long long)key);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * kSortBins; i += kSortThreads)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
-__global__ void k_voxel_finalize(const double* __restrict__ sums, const int* __restrict__ counts, const int* __restrict__ nv_ptr, VoxelRec* __restrict__ vox) {  // :158-176
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= *nv_ptr) return;  // launched for an upper bound; the voxel count is still on the device
-  int c = counts[v];
-  double inv = 1.0 / (double)c;
-  const double* d = sums + (size_t)v * 10;
-  VoxelRec r;
-  r.mean_n = make_float4((float)(d[0] * inv), (float)(d[1] * inv), (float)(d[2] * inv), __int_as_float(c));
-  r.c0 = make_float4((float)(d[3] * inv), (float)(d[4] * inv), (float)(d[5] * inv), (float)(d[6] * inv));
-  r.c1 = make_float4((float)(d[7] * inv), (float)(d[8] * inv), 0.f, 0.f);
-  vox[v] = r;
+// [start, end) of every voxel in the sorted list
+__global__ void k_voxel_segments(const unsigned* __restrict__ keys, int n, unsigned invalid, int2* __restrict__ seg) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned key = keys[j];
+  if (key == invalid) return;
+  if (j == 0 || keys[j - 1] != key) seg[key].x = j;
+  if (j == n - 1 || keys[j + 1] != key) seg[key].y = j + 1;
 }
 
-// NDT voxel maps are built from the points alone (gaussian_voxelmap.cu:122-148): sums of p and p p^T (double, order-free)
-__global__ void k_voxel_accumulate_ndt(const float4* __restrict__ pts, int n, const int* __restrict__ slot_of_point, const int4* __restrict__ buckets, double* __restrict__ sums,
-                                       int* __restrict__ counts) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int s = slot_of_point[i];
-  if (s < 0) return;
-  int id = buckets[s].w;
-  float4 p = pts[i];
-  double x = (double)p.x, y = (double)p.y, z = (double)p.z;
-  double* d = sums + (size_t)id * 10;
-  atomicAdd(&counts[id], 1);
-  atomicAdd(d + 0, x); atomicAdd(d + 1, y); atomicAdd(d + 2, z);
-  atomicAdd(d + 3, x * x); atomicAdd(d + 4, x * y); atomicAdd(d + 5, x * z);
-  atomicAdd(d + 6, y * y); atomicAdd(d + 7, y * z); atomicAdd(d + 8, z * z);
-}
-
-// ndt_finalize_voxels_kernel (gaussian_voxelmap.cu:178-198): mean = sum/n ; cov = (sum_ppT - mean * sum^T) / n
-__global__ void k_voxel_finalize_ndt(const double* __restrict__ sums, const int* __restrict__ counts, const int* __restrict__ nv_ptr, VoxelRec* __restrict__ vox) {
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per voxel.  Lane c < 10 carries one sum: 0..2 the point, 3..8 the covariance terms (xx xy xz yy yz zz; VGICP: the
+// point's packed covariance, NDT: p p^T formed in double), 9 nothing (the count is the segment length).
+template <bool NDT>
+__global__ void __launch_bounds__(128) k_voxel_reduce(const float4* __restrict__ pts, const float4* __restrict__ covA, const float2* __restrict__ covB, const unsigned* __restrict__ order,
+                                                      const int2* __restrict__ seg, const int* __restrict__ nv_ptr, VoxelRec* __restrict__ vox) {
+  const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (v >= *nv_ptr) return;
-  int c = counts[v];
-  double nn = (double)c;
-  const double* d = sums + (size_t)v * 10;
-  double mx = d[0] / nn, my = d[1] / nn, mz = d[2] / nn;
-  VoxelRec r;
-  r.mean_n = make_float4((float)mx, (float)my, (float)mz, __int_as_float(c));
-  r.c0 = make_float4((float)((d[3] - mx * d[0]) / nn), (float)((d[4] - my * d[0]) / nn), (float)((d[5] - mz * d[0]) / nn), (float)((d[6] - my * d[1]) / nn));
-  r.c1 = make_float4((float)((d[7] - mz * d[1]) / nn), (float)((d[8] - mz * d[2]) / nn), 0.f, 0.f);
-  vox[v] = r;
+  const int2 se = seg[v];
+  const int c = lane < 9 ? lane : 0;
+  // component c of point i as a double
+  auto term = [&](unsigned i) -> double {
+    const float* p = reinterpret_cast<const float*>(pts + i);
+    if (c < 3) return (double)p[c];
+    if (NDT) {  // xx xy xz yy yz zz
+      const int t = c - 3;
+      const int r0 = t < 3 ? 0 : (t < 5 ? 1 : 2), c0 = t < 3 ? t : (t < 5 ? t - 2 : 2);
+      return (double)p[r0] * (double)p[c0];
+    }
+    if (c < 7) return (double)reinterpret_cast<const float*>(covA + i)[c - 3];
+    return (double)reinterpret_cast<const float*>(covB + i)[c - 7];
+  };
+  double sum = 0.0;
+  int j = se.x;
+  for (; j + 4 <= se.y; j += 4) {  // four gathers in flight, added in order
+    const unsigned i0 = order[j], i1 = order[j + 1], i2 = order[j + 2], i3 = order[j + 3];
+    const double t0 = term(i0), t1 = term(i1), t2 = term(i2), t3 = term(i3);
+    sum += t0; sum += t1; sum += t2; sum += t3;
+  }
+  for (; j < se.y; j++) sum += term(order[j]);
+  const int cnt = se.y - se.x;
+  const double nn = (double)cnt;
+  float out;
+  if (NDT) {  // mean = sum / n ; cov(r, c) = (S_rc - mean_r * S_c) / n, lower triangle in the packed record
+    const double sx = __shfl_sync(0xffffffffu, sum, 0), sy = __shfl_sync(0xffffffffu, sum, 1), sz = __shfl_sync(0xffffffffu, sum, 2);
+    const double mx = sx / nn, my = sy / nn, mz = sz / nn;
+    // (spelled with intrinsics: a contracted fma would round differently from the checker's multiply-then-subtract)
+    double val = sum / nn;
+    if (c >= 3) {
+      const double m_r = c == 3 ? mx : (c == 4 || c == 6 ? my : mz);
+      const double s_c = c <= 5 ? sx : (c <= 7 ? sy : sz);
+      val = __ddiv_rn(__dsub_rn(sum, __dmul_rn(m_r, s_c)), nn);
+    }
+    out = (float)val;
+  } else {
+    out = (float)(sum / nn);
+  }
+  // record layout: {mx my mz n} {cxx cxy cxz cyy} {cyz czz 0 0}: lane c < 3 -> float c, lanes 3..8 -> floats 4..9, lane 9 -> n, lanes 10, 11 -> 0
+  float* rec = reinterpret_cast<float*>(vox + v);
+  if (lane < 3) rec[lane] = out;
+  else if (lane < 9) rec[lane + 1] = out;
+  else if (lane == 9) rec[3] = __int_as_float(cnt);
+  else if (lane < 12) rec[lane] = 0.f;
 }
 
 // D2D: the source voxel means / covariances become the "source cloud" of the evaluation kernel

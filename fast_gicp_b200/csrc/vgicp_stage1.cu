@@ -7,6 +7,7 @@
 // line-like neighbourhoods (lidar rings) into percent-level differences of the covariance, so "close" is not
 // good enough here.
 #include "vgicp_stage1.cuh"
+#include "vgicp_sort.cuh"
 
 #include <math.h>
 #include <stdint.h>
@@ -254,16 +255,64 @@ __global__ void __launch_bounds__(128) k_covariance_knn(const float4* __restrict
   store_cov_sym(c, covA, covB, i);
 }
 
-// Stage 1b': covariance_estimation_rbf.cu:59-151.  One query per thread, all points streamed through shared memory in
-// blocks of 512 like the reference's per-block async transforms; partial sums per 512-block are folded in block order
-// (the reference's strided finalisation, :92-114).  The reference pads the cloud to a multiple of 512 with points at the
-// origin (:126-129) which pick up weight whenever the query is within max_dist of the origin -- reproduced.
-// All nine entries of sum w p p^T are kept ((w p_r) p_c and (w p_c) p_r round differently and the reference's Matrix3f holds
-// both).  The weight is exp evaluated in double and rounded once: the reference calls CUDA's 2-ulp expf, which no CPU checker can
-// reproduce bit for bit; the correctly rounded value lies within that function's own error bound and makes the stage testable
-// bit-for-bit like the rest of this file.
-__global__ void __launch_bounds__(128) k_covariance_rbf(const float4* __restrict__ pts, int n, float exp_factor, float max_dist, int method, float4* __restrict__ covA,
-                                                       float2* __restrict__ covB) {
+// exp(x) for x <= 0 from IEEE single operations only (Cephes' expf: n = rint(x log2 e), two-step reduction r = x - n ln 2,
+// degree-5 polynomial, scale by 2^n), every operation spelled, so that the CPU checker evaluates the identical sequence.
+// Why not expf: the reference calls CUDA's expf, a 2-ulp function that no CPU libm reproduces bit for bit; this one has the same
+// accuracy class (about 1 ulp) and makes the RBF stage testable bit-for-bit like the rest of this file.
+__device__ __forceinline__ float exp_det(float x) {
+  if (x < -87.0f) return 0.0f;
+  const float n = rintf(__fmul_rn(x, 1.44269504088896341f));
+  float r = __fmaf_rn(n, -0.693359375f, x);
+  r = __fmaf_rn(n, 2.12194440e-4f, r);
+  float p = 1.9875691500e-4f;
+  p = __fmaf_rn(p, r, 1.3981999507e-3f);
+  p = __fmaf_rn(p, r, 8.3334519073e-3f);
+  p = __fmaf_rn(p, r, 4.1665795894e-2f);
+  p = __fmaf_rn(p, r, 1.6666665459e-1f);
+  p = __fmaf_rn(p, r, 5.0000001201e-1f);
+  p = __fadd_rn(__fmaf_rn(p, __fmul_rn(r, r), r), 1.0f);
+  return __fmul_rn(p, __int_as_float(((int)n + 127) << 23));
+}
+
+// bounding boxes of the 512-point blocks of the (zero-padded) cloud: box[b] = {min xyz, max xyz}
+__global__ void __launch_bounds__(128) k_rbf_block_boxes(const float4* __restrict__ pts, int n, float* __restrict__ boxes) {
+  __shared__ float red[4][6];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float lo[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+  float hi[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+  for (int j = tid; j < kRbfBlock; j += 128) {
+    const int g = b * kRbfBlock + j;
+    const float4 p = g < n ? pts[g] : make_float4(0.f, 0.f, 0.f, 0.f);  // the padding sits at the origin (:126-129)
+    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+  if ((tid & 31) == 0)
+    for (int d = 0; d < 3; d++) { red[tid >> 5][d] = lo[d]; red[tid >> 5][3 + d] = hi[d]; }
+  __syncthreads();
+  if (tid < 6) {
+    float v = red[0][tid];
+    for (int w = 1; w < 4; w++) v = tid < 3 ? fminf(v, red[w][tid]) : fmaxf(v, red[w][tid]);
+    boxes[b * 6 + tid] = v;
+  }
+}
+
+// Stage 1b': covariance_estimation_rbf.cu:59-151.  One query per thread, the points streamed through shared memory in blocks of 512
+// like the reference's per-block async transforms; partial sums per 512-block are folded in block order (the reference's strided
+// finalisation, :92-114).  The reference pads the cloud to a multiple of 512 with points at the origin (:126-129) which pick up
+// weight whenever the query is within max_dist of the origin -- reproduced.  All nine entries of sum w p p^T are kept ((w p_r) p_c
+// and (w p_c) p_r round differently and the reference's Matrix3f holds both).
+// A block whose bounding box is farther than max_dist from the query contributes an all-zero partial (x + 0 == x): it is skipped, and
+// a tile no query of the thread block needs is not even staged.  Scan-ordered LiDAR blocks are compact arcs, so ~90 % are skipped;
+// the float box distance uses the same operations as the per-point distance and rounding is monotone, so it never exceeds it.
+__global__ void __launch_bounds__(128) k_covariance_rbf(const float4* __restrict__ pts, int n, float exp_factor, float max_dist, int method, const float* __restrict__ boxes,
+                                                       float4* __restrict__ covA, float2* __restrict__ covB) {
   __shared__ float4 tile[kRbfBlock];
   const int tid = threadIdx.x;
   const int q = blockIdx.x * blockDim.x + tid;
@@ -273,20 +322,26 @@ __global__ void __launch_bounds__(128) k_covariance_rbf(const float4* __restrict
   float sw = 0.f, m[3] = {0.f, 0.f, 0.f}, c[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // c: row-major
   const int nblocks = (n + kRbfBlock - 1) / kRbfBlock;
   for (int b = 0; b < nblocks; b++) {
-    __syncthreads();
+    bool need = false;
+    if (active) {
+      const float* bx = boxes + b * 6;
+      const float dx = fmaxf(fmaxf(bx[0] - x.x, x.x - bx[3]), 0.f), dy = fmaxf(fmaxf(bx[1] - x.y, x.y - bx[4]), 0.f), dz = fmaxf(fmaxf(bx[2] - x.z, x.z - bx[5]), 0.f);
+      need = !((dx * dx + dy * dy) + dz * dz > max_dist_sq);
+    }
+    if (!__syncthreads_or(need)) continue;  // (also orders the previous tile's reads before the next staging)
     for (int j = tid; j < kRbfBlock; j += blockDim.x) {
       int g = b * kRbfBlock + j;
       tile[j] = g < n ? pts[g] : make_float4(0.f, 0.f, 0.f, 0.f);  // padding at the origin, :126-129
     }
     __syncthreads();
-    if (!active) continue;
+    if (!need) continue;
     float psw = 0.f, pm[3] = {0.f, 0.f, 0.f}, pc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < kRbfBlock; j++) {
       float4 p = tile[j];
       float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
       float sq = (dx * dx + dy * dy) + dz * dz;
       if (sq > max_dist_sq) continue;
-      float w = (float)exp((double)(-exp_factor * sq));
+      float w = exp_det(-exp_factor * sq);
       psw += w;
       float wx = w * p.x, wy = w * p.y, wz = w * p.z;
       pm[0] += wx; pm[1] += wy; pm[2] += wz;
@@ -314,44 +369,49 @@ __global__ void __launch_bounds__(128) k_covariance_rbf(const float4* __restrict
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Stage 1a': exact k-NN on a multi-level hash grid, one warp per query.
+// Stage 1a': exact k-NN on a Morton-ordered multi-level grid, one THREAD per query.
 //
-// Why: lidar clouds are surfaces with a density that falls with range; the 20-NN radius spans 0.2 m .. several metres.
-// A ladder of L uniform grids (cell size s_l = s_max / 2^(L-1-l), s_max = extent/4) is built in three launches
-// (count / allocate / scatter, every point inserted at every level); a query walks the ladder from the finest level
-// and stops at the first level where the 3x3x3 (or 5x5x5) block around its cell provably contains its k nearest
-// neighbours: every point within r*s of the query lies inside the (2r+1)^3 block, so kth_d2 <= (r*s)^2 certifies it.
-// If even the coarsest level cannot certify (tiny clouds, far outliers) the warp scans the whole cloud.
+// Why: lidar clouds are surfaces whose density falls with range; the 20-NN radius spans 0.2 m .. several metres, so no single
+// cell size fits.  The points are sorted ONCE by the Morton code of their finest cell (cell size s_0 = extent / 2^(L+1)); a cell
+// of level l (size s_0 * 2^l) is then a contiguous run of the sorted array, and one hash table maps (level, cell) -> [start, end).
+// The table is filled from the sorted codes alone (a point starts / ends the cells of every level at which its code differs
+// from its predecessor's / successor's): no per-level scatter, one sorted copy of the cloud for all levels.
 //
-// Selection: the warp keeps the k best (d2, index) pairs sorted across its lanes (rank r in lane r%32, register
-// r/32); a batch of 32 candidates is loaded coalesced from the cell-sorted copy, lanes whose candidate beats the
-// current worst are inserted one at a time with ballot + shuffle (no shared memory, no divergence between queries).
-// Ties are ordered by index, so the result is the unique ascending (d2, index) list -- identical to the CPU checker.
+// Query (thread i = sorted position i, so the threads of a warp are spatial neighbours and mostly walk the same cells):
+//   1. the 2k+1 points around position i in Morton order seed a max-heap of the k best (d2, index) keys -> an upper bound B on
+//      the k-th distance;
+//   2. the finest level l with 0.999 s_l >= B: every point within B of the query lies in the 3x3x3 block of its cell there;
+//   3. the block's cells whose box lies within the (shrinking) k-th distance are looked up and scanned, skipping the window.
+// That is exact by construction (no certificate, no restart).  Blocks with very many candidates and queries whose bound exceeds
+// the coarsest level (tiny clouds, far outliers) are handed to a block-cooperative kernel.
+// Top-k: a binary max-heap of 64-bit keys ((bits of d2) << 32 | index; d2 >= 0, so unsigned order == ascending (d2, index)) in
+// shared memory, [k][thread] (bank = thread: conflict-free whatever heap slot each lane touches); heap-sorted in place at the
+// end, so rows come out as the unique ascending (d2, index) list -- identical to the CPU checker.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kGridMaxLevels = 12;
 constexpr unsigned long long kGridEmpty = 0xFFFFFFFFFFFFFFFFULL;
 
-struct GridLevel {
-  unsigned long long* keys;  // [T] packed cell coordinate, kGridEmpty when free
-  int* cnt;                  // [T] points in the cell
-  int* start;                // [T] first index of the cell in `sorted`
-  int* fill;                 // [T] scatter cursor
-  float4* sorted;            // [n] points grouped by cell, original index in .w
-  int* pslot;                // [n] table slot of each point (count pass -> scatter pass)
+struct __align__(16) CellEntry {
+  unsigned long long key;  // (Morton prefix of the cell << 4) | level, kGridEmpty when free
+  unsigned start, end;     // the cell's points are sorted[start .. end)
 };
 
 struct GridArgs {
   const float4* pts;
   int n, k, L;
-  unsigned tmask;            // table size - 1 (same for every level)
-  unsigned* bbox_min;        // [3] ordered-uint min xyz (initialised to 0xFFFFFFFF)
-  unsigned* bbox_max;        // [3] ordered-uint max xyz (initialised to 0)
-  int* level_cursor;         // [L]
-  int* query_cursor;         // work counter of the query kernel
-  int* heavy_count;          // number of queries deferred to the block-cooperative kernel
-  int* heavy_cursor;         // its work counter
-  int2* heavy_queue;         // [n] (position in lv[0].sorted, level to resume at)
-  GridLevel lv[kGridMaxLevels];
+  unsigned* bbox_min;          // [3] ordered-uint min xyz (initialised to 0xFFFFFFFF)
+  unsigned* bbox_max;          // [3] ordered-uint max xyz (initialised to 0)
+  unsigned long long* codes;   // [n] Morton codes of the finest cells, sorted
+  float4* sorted;              // [n] points in that order, original index in .w
+  CellEntry* table;
+  unsigned tmask;
+  int* level_hist;             // [kGridMaxLevels + 2] histogram over the points of "first level shared with the predecessor"
+  int* l_min;                  // finest level present in the table
+  unsigned* done_blocks;       // ticket of k_grid_levels
+  int* defer_count;            // queries handed to the block-cooperative kernel
+  int* defer_cursor;
+  int2* defer_queue;           // [n] (sorted position, level of the block to scan; L = whole cloud)
+  int q_begin, q_end;          // sorted positions searched by this launch (multi-GPU: a slice per rank)
   int* nbr;
 };
 
@@ -388,110 +448,343 @@ __global__ void k_grid_bbox(const float4* __restrict__ pts, int n, unsigned* __r
 
 struct GridGeom {
   float minx, miny, minz;
-  float s_max;
+  float s0, inv_s0;  // finest cell size
+  int cmax;          // largest cell coordinate of the finest level: 2^(L+1) - 1
 };
-__device__ __forceinline__ GridGeom grid_geom(const unsigned* __restrict__ bmin, const unsigned* __restrict__ bmax) {
+__device__ __forceinline__ GridGeom grid_geom(const unsigned* __restrict__ bmin, const unsigned* __restrict__ bmax, int L) {
   GridGeom g;
   g.minx = ord2f(bmin[0]); g.miny = ord2f(bmin[1]); g.minz = ord2f(bmin[2]);
   float ex = ord2f(bmax[0]) - g.minx, ey = ord2f(bmax[1]) - g.miny, ez = ord2f(bmax[2]) - g.minz;
   float e = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-3f));
-  g.s_max = e * 0.25f;
+  g.s0 = ldexpf(e, -(L + 1));  // coarsest level: 4 cells along the longest axis
+  g.inv_s0 = 1.0f / g.s0;
+  g.cmax = (2 << L) - 1;
   return g;
 }
-__device__ __forceinline__ float grid_cell_size(const GridGeom& g, int l, int L) { return ldexpf(g.s_max, l - (L - 1)); }
-__device__ __forceinline__ int3 grid_cell(const GridGeom& g, float inv_s, float x, float y, float z) {
-  return make_int3((int)floorf((x - g.minx) * inv_s), (int)floorf((y - g.miny) * inv_s), (int)floorf((z - g.minz) * inv_s));
+// finest-level cell of a point; the far face of the bounding box is clamped into the last cell (its box is closed there)
+__device__ __forceinline__ int3 grid_cell0(const GridGeom& g, float x, float y, float z) {
+  int cx = (int)floorf((x - g.minx) * g.inv_s0), cy = (int)floorf((y - g.miny) * g.inv_s0), cz = (int)floorf((z - g.minz) * g.inv_s0);
+  return make_int3(min(max(cx, 0), g.cmax), min(max(cy, 0), g.cmax), min(max(cz, 0), g.cmax));
 }
-__device__ __forceinline__ unsigned long long grid_key(int x, int y, int z) {  // 21 bits per axis, offset so that -1 is representable
-  return ((unsigned long long)(unsigned)(x + 1024) << 42) | ((unsigned long long)(unsigned)(y + 1024) << 21) | (unsigned long long)(unsigned)(z + 1024);
+__device__ __forceinline__ unsigned long long spread3(unsigned v) {  // bit i of v -> bit 3 i
+  unsigned long long x = v & 0x1fffffu;
+  x = (x | x << 32) & 0x1f00000000ffffULL;
+  x = (x | x << 16) & 0x1f0000ff0000ffULL;
+  x = (x | x << 8) & 0x100f00f00f00f00fULL;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+  x = (x | x << 2) & 0x1249249249249249ULL;
+  return x;
 }
+__device__ __forceinline__ unsigned long long morton3(int x, int y, int z) { return (spread3((unsigned)x) << 2) | (spread3((unsigned)y) << 1) | spread3((unsigned)z); }
 __device__ __forceinline__ unsigned grid_hash(unsigned long long k) {
   k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
   return (unsigned)k;
 }
+// first level at which two finest-cell codes fall into the same cell (0 when equal)
+__device__ __forceinline__ int shared_level(unsigned long long a, unsigned long long b) {
+  const unsigned long long x = a ^ b;
+  return x ? (63 - __clzll((long long)x)) / 3 + 1 : 0;
+}
 
-// count pass: thread per (level, point).  Consecutive points are spatially coherent (scan order), so most lanes of a
-// warp fall into the same cell, above all on the coarse levels: lanes with equal keys elect a leader that does the
-// table probe and one atomicAdd for the group (same-address atomics serialise in L2).
-__global__ void k_grid_count(GridArgs a) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int l = blockIdx.y;
-  const bool active = i < a.n;
-  GridGeom g = grid_geom(a.bbox_min, a.bbox_max);
-  float inv_s = 1.0f / grid_cell_size(g, l, a.L);
-  float4 p = a.pts[active ? i : 0];
-  int3 c = grid_cell(g, inv_s, p.x, p.y, p.z);
-  unsigned long long key = active ? grid_key(c.x, c.y, c.z) : kGridEmpty;
-  GridLevel lv = a.lv[l];
-  const unsigned peers = __match_any_sync(0xffffffffu, key);
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(peers) - 1;
-  unsigned pos = 0;
-  if (active && lane == leader) {
-    pos = grid_hash(key) & a.tmask;
-    for (;;) {
-      unsigned long long cur = lv.keys[pos];
-      if (cur == kGridEmpty) {
-        unsigned long long old = atomicCAS(&lv.keys[pos], kGridEmpty, key);
-        cur = (old == kGridEmpty) ? key : old;
-      }
-      if (cur == key) break;
-      pos = (pos + 1) & a.tmask;
+// Morton codes of the finest cells + the digit histograms of the sort
+__global__ void __launch_bounds__(kSortThreads) k_grid_codes(GridArgs a, int passes, unsigned* __restrict__ hist) {
+  __shared__ unsigned sh[kSortMaxPasses * kSortBins];
+  for (int i = threadIdx.x; i < passes * kSortBins; i += kSortThreads) sh[i] = 0;
+  __syncthreads();
+  const GridGeom g = grid_geom(a.bbox_min, a.bbox_max, a.L);
+  const int n_round = (a.n + 31) & ~31;
+  for (int i = blockIdx.x * kSortThreads + threadIdx.x; i < n_round; i += gridDim.x * kSortThreads) {
+    const bool valid = i < a.n;
+    unsigned long long code = 0;
+    if (valid) {
+      const float4 p = a.pts[i];
+      const int3 c = grid_cell0(g, p.x, p.y, p.z);
+      code = morton3(c.x, c.y, c.z);
+      a.codes[i] = code;
     }
-    atomicAdd(&lv.cnt[pos], __popc(peers));
+    sort_hist_add(sh, passes, valid, code);
   }
-  pos = __shfl_sync(0xffffffffu, pos, leader);
-  if (active) lv.pslot[i] = (int)pos;
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * kSortBins; i += kSortThreads)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
-// allocate pass: thread per (level, slot): carve the cell's range out of the level's sorted array (one atomic per warp)
-__global__ void k_grid_alloc(GridArgs a) {
-  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  int l = blockIdx.y;
-  GridLevel lv = a.lv[l];
-  const int lane = threadIdx.x & 31;
-  int c = (t <= a.tmask) ? lv.cnt[t] : 0;
-  int incl = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
+// cells per level (from the sorted codes) -> the finest level whose cells, together with all coarser ones, fit half the table
+__global__ void __launch_bounds__(256) k_grid_levels(GridArgs a) {
+  __shared__ int sh[kGridMaxLevels + 2];
+  __shared__ bool is_last;
+  if (threadIdx.x < kGridMaxLevels + 2) sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+    const int ld = i > 0 ? min(shared_level(a.codes[i], a.codes[i - 1]), a.L) : a.L;  // starts a cell at every level below ld
+    atomicAdd(&sh[ld], 1);
   }
-  int total = __shfl_sync(0xffffffffu, incl, 31);
-  if (total == 0) return;
-  int base = 0;
-  if (lane == 31) base = atomicAdd(&a.level_cursor[l], total);
-  base = __shfl_sync(0xffffffffu, base, 31);
-  if (c > 0) lv.start[t] = base + incl - c;
+  __syncthreads();
+  if (threadIdx.x < kGridMaxLevels + 2 && sh[threadIdx.x]) atomicAdd(&a.level_hist[threadIdx.x], sh[threadIdx.x]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(a.done_blocks, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  // cells of level l = points with ld > l; walk from the coarsest level down while the total stays within half the table
+  const long long cap = ((long long)a.tmask + 1) / 2;
+  long long cells = 0, total = 0;
+  int l_min = a.L - 1;
+  for (int l = a.L - 1; l >= 0; l--) {
+    cells += *reinterpret_cast<volatile int*>(&a.level_hist[l + 1]);
+    if (total + cells > cap && l < a.L - 1) break;
+    total += cells;
+    l_min = l;
+  }
+  *a.l_min = l_min;
 }
 
-// scatter pass: thread per (level, point), one cursor atomic per group of lanes sharing a cell
-__global__ void k_grid_scatter(GridArgs a) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int l = blockIdx.y;
-  const bool active = i < a.n;
-  GridLevel lv = a.lv[l];
-  const int lane = threadIdx.x & 31;
-  int slot = active ? lv.pslot[i] : -1 - lane;  // inactive lanes get unique keys
-  const unsigned peers = __match_any_sync(0xffffffffu, slot);
-  const int leader = __ffs(peers) - 1;
-  int base = 0;
-  if (active && lane == leader) base = lv.start[slot] + atomicAdd(&lv.fill[slot], __popc(peers));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (!active) return;
-  int rank = __popc(peers & ((1u << lane) - 1u));
-  float4 p = a.pts[i];
-  p.w = __int_as_float(i);
-  lv.sorted[base + rank] = p;
+// table fill: position i opens the cells of the levels at which its code differs from its predecessor's and closes those at
+// which it differs from its successor's.  The opener and the closer of a cell find the same slot (insert-or-find by CAS on the key)
+// and write different fields of it.
+__device__ __forceinline__ CellEntry* table_slot(const GridArgs& a, unsigned long long key) {
+  unsigned pos = grid_hash(key) & a.tmask;
+  for (;;) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&a.table[pos].key);
+    if (cur == kGridEmpty) {
+      const unsigned long long old = atomicCAS(&a.table[pos].key, kGridEmpty, key);
+      cur = (old == kGridEmpty) ? key : old;
+    }
+    if (cur == key) return &a.table[pos];
+    pos = (pos + 1) & a.tmask;
+  }
+}
+__global__ void __launch_bounds__(256) k_grid_table(GridArgs a) {  // blockIdx.y = level - l_min: a thread per (point, level), two slot operations at most
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = *a.l_min + (int)blockIdx.y;
+  if (i >= a.n || l >= a.L) return;
+  const unsigned long long c = a.codes[i];
+  const int ls = i > 0 ? min(shared_level(c, a.codes[i - 1]), a.L) : a.L;
+  const int le = i + 1 < a.n ? min(shared_level(c, a.codes[i + 1]), a.L) : a.L;
+  if (l >= ls && l >= le) return;
+  CellEntry* e = table_slot(a, ((c >> (3 * l)) << 4) | (unsigned)l);
+  if (l < ls) e->start = (unsigned)i;
+  if (l < le) e->end = (unsigned)i + 1u;
 }
 
-// ---- warp-level sorted top-k (k <= 64): rank r lives in lane r & 31, register r >> 5.
-// An entry is one 64-bit key: (bits of d2) << 32 | index.  d2 >= 0, so unsigned order of the key == ascending (d2, index).
-// WIDE=false (k <= 32) keeps a single register set. ----
+__device__ __forceinline__ bool cell_range(const GridArgs& a, unsigned long long key, int& start, int& end) {
+  unsigned pos = grid_hash(key) & a.tmask;
+  for (;;) {
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(&a.table[pos]));
+    const unsigned long long cur = ((unsigned long long)e.y << 32) | e.x;
+    if (cur == key) { start = (int)e.z; end = (int)e.w; return true; }
+    if (cur == kGridEmpty) return false;
+    pos = (pos + 1) & a.tmask;
+  }
+}
+
 typedef unsigned long long tkey;
 constexpr tkey kKeyInf = 0x7f8000007fffffffULL;  // (+inf, INT_MAX)
 __device__ __forceinline__ tkey make_key(float d, int i) { return ((tkey)__float_as_uint(d) << 32) | (unsigned)i; }
+__device__ __forceinline__ int key_index(tkey e) { return (int)(unsigned)(e & 0xffffffffULL); }
+__device__ __forceinline__ float knn_d2(float4 q, float4 t) {  // (dx*dx + dy*dy) + dz*dz, no contraction
+  float dx = __fsub_rn(t.x, q.x), dy = __fsub_rn(t.y, q.y), dz = __fsub_rn(t.z, q.z);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
 
+constexpr int kSearchThreads = 128;
+constexpr int kDeferCandidates = 768;  // blocks with more candidates than this go to the block-cooperative kernel (~1 % of the queries of a
+                                       // LiDAR scan: density transitions, where a lone thread would stall its warp for thousands of points)
+// nearest-first order of the 3x3x3 block (index = 9*(dx+1) + 3*(dy+1) + (dz+1)): centre, 6 faces, 12 edges, 8 corners
+__constant__ unsigned char kBlockOrder[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25, 0, 2, 6, 8, 18, 20, 24, 26};
+
+// Per-thread candidate buffer in shared memory, [slot][thread] (bank = thread: conflict-free whatever slot each lane touches).
+// Everything a thread does with it is a plain counted loop -- count the keys below a threshold, compact, rank -- so the lanes of a
+// warp stay converged and the loops have instruction-level parallelism (a heap or a sorted insertion would be a dependent chain of
+// shared-memory accesses behind a branch that some lane of the warp takes at almost every candidate).
+#define KNN_BUF(j) buf[(j) * kSearchThreads + threadIdx.x]
+#define KNN_BUF_HI(j) reinterpret_cast<const unsigned*>(buf)[((j) * kSearchThreads + threadIdx.x) * 2 + 1]
+
+// Smallest-ish threshold T on the distance bits (the high word of the keys) such that at least k of the cnt buffered keys have
+// distance bits <= T: bisection on the bit pattern (non-negative floats order like their bits), stopping early once at most
+// k + slack keys qualify.  `hi` must qualify on entry (count(<= hi) >= k).
+__device__ __noinline__ unsigned tighten_threshold(const tkey* buf, int cnt, int k, int slack, unsigned hi) {
+  unsigned lo = 0;
+  while (hi - lo > 1u) {
+    const unsigned mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+    for (int j = 0; j < cnt; j++) c += KNN_BUF_HI(j) <= mid ? 1 : 0;
+    if (c >= k) {
+      hi = mid;
+      if (c <= k + slack) break;
+    } else {
+      lo = mid;
+    }
+  }
+  return hi;
+}
+// keep the keys whose distance bits are <= T (stable, in place); returns the new count
+__device__ __noinline__ int compact_below(tkey* buf, int cnt, unsigned T) {
+  int w = 0;
+  for (int j = 0; j < cnt; j++) {
+    const tkey e = KNN_BUF(j);
+    if ((unsigned)(e >> 32) <= T) KNN_BUF(w++) = e;
+  }
+  return w;
+}
+
+// candidates sorted[st .. en): those within the bound T are appended to the buffer (four loads in flight); a full buffer is tightened
+// to (about) the k-th distance of what it holds.  Returns the new count, or -1 when the buffer cannot be tightened (ties).
+// Not inlined: the caller's nine-cell rounds are unrolled, and nine copies of this body would not fit the instruction cache.
+__device__ __noinline__ int scan_cell(tkey* buf, int cnt, unsigned& T, float4 q, const float4* __restrict__ sorted, int st, int en, int k, int cap) {
+  for (int p0 = st; p0 < en; p0 += 4) {
+    float4 c[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) c[u] = __ldg(&sorted[min(p0 + u, en - 1)]);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const float d2 = knn_d2(q, c[u]);
+      if (p0 + u < en && __float_as_uint(d2) <= T) {
+        KNN_BUF(cnt) = make_key(d2, __float_as_int(c[u].w));
+        cnt++;
+      }
+    }
+    if (cnt > cap - 4) {
+      T = tighten_threshold(buf, cnt, k, (k >> 3) + 1, T);
+      cnt = compact_below(buf, cnt, T);
+      if (cnt > cap - 8) return -1;
+    }
+  }
+  return cnt;
+}
+
+__device__ __forceinline__ unsigned long long sel3(const unsigned long long* v, int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]); }  // (selects, not a dynamic index)
+
+// finest level l >= l_min with 0.998 s_l >= B (L when there is none); s = that level's cell size
+__device__ __forceinline__ int level_for(float B, int l_min, int L, float s0, float& s) {
+  int l = l_min;
+  s = ldexpf(s0, l);
+  while (l < L && !(B <= 0.998f * s)) { l++; s *= 2.0f; }  // (also runs to L when B is inf / NaN)
+  return l;
+}
+
+__global__ void __launch_bounds__(kSearchThreads, 3) k_knn_search(GridArgs a, int cap, int force_whole_cloud) {
+  extern __shared__ tkey buf[];  // [cap][kSearchThreads]
+  const int i = a.q_begin + blockIdx.x * kSearchThreads + threadIdx.x;
+  if (i >= a.q_end) return;
+  const int k = a.k, L = a.L;
+  const GridGeom g = grid_geom(a.bbox_min, a.bbox_max, L);
+  const float4 q = __ldg(&a.sorted[i]);
+  const int qi = __float_as_int(q.w);
+  if (force_whole_cloud) {
+    a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, L);
+    return;
+  }
+  // 1. Morton window: the k-th smallest of the distances to the ~3k points around position i bounds the k-th distance from above
+  unsigned T;  // threshold on the distance bits; invariant: at least k points of the cloud have distance bits <= T
+  {
+    const int h = min(k + (k >> 1) < 8 ? 8 : k + (k >> 1), (cap - 1) / 2);
+    int wlo = i - h, whi = i + h;
+    if (wlo < 0) { whi -= wlo; wlo = 0; }
+    if (whi > a.n - 1) { wlo -= whi - (a.n - 1); whi = a.n - 1; }
+    if (wlo < 0) wlo = 0;
+    const int cnt = whi - wlo + 1;  // >= k (n >= k, h >= k)
+    unsigned mx = 0;
+    for (int j = 0; j < cnt; j++) {
+      const float4 c = __ldg(&a.sorted[wlo + j]);
+      const tkey key = make_key(knn_d2(q, c), __float_as_int(c.w));
+      KNN_BUF(j) = key;
+      mx = max(mx, (unsigned)(key >> 32));
+    }
+    T = tighten_threshold(buf, cnt, k, (k >> 3) + 1, mx);
+  }
+  const int l_min = *a.l_min;
+  float s;
+  const int l = level_for(sqrtf(__uint_as_float(T)), l_min, L, g.s0, s);
+  if (l >= L) {  // the bound exceeds the coarsest cells (tiny cloud, far outlier): whole cloud, block-cooperative
+    a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, L);
+    return;
+  }
+  // 2. the 3x3x3 block of that level holds every point within the bound of the query (window points included): the cells whose box
+  //    lies within the bound are scanned, candidates within the bound are appended to the buffer
+  const int3 c0 = grid_cell0(g, q.x, q.y, q.z);
+  const int cqx = c0.x >> l, cqy = c0.y >> l, cqz = c0.z >> l, cl_max = g.cmax >> l;
+  const float fx = q.x - g.minx, fy = q.y - g.miny, fz = q.z - g.minz;
+  const float slack = 2e-3f * s;  // rounding of the cell boundaries
+  // Morton bits of the three cell coordinates per axis (a neighbour's code is an OR of three of them)
+  unsigned long long mx[3], my[3], mz[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    mx[d] = spread3((unsigned)(cqx + d - 1)) << 2;
+    my[d] = spread3((unsigned)(cqy + d - 1)) << 1;
+    mz[d] = spread3((unsigned)(cqz + d - 1));
+  }
+  int cnt = 0, scanned = 0;
+#pragma unroll 1
+  for (int b = 0; b < 3; b++) {  // nine cells per round: their table probes are in flight together
+    uint4 e[9];
+    unsigned long long ckey[9];
+    float box2[9];
+    bool want[9];
+    {
+      const float reach = sqrtf(__uint_as_float(T)) + slack;
+      const float reach2 = reach * reach;
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        const int oo = kBlockOrder[b * 9 + j];
+        const int cx = cqx + oo / 9 - 1, cy = cqy + (oo / 3) % 3 - 1, cz = cqz + oo % 3 - 1;
+        // distance from the query to the cell's box against the bound (+ slack)
+        const float lx = cx * s, ly = cy * s, lz = cz * s;
+        const float ex = fmaxf(fmaxf(lx - fx, fx - (lx + s)), 0.f), ey = fmaxf(fmaxf(ly - fy, fy - (ly + s)), 0.f), ez = fmaxf(fmaxf(lz - fz, fz - (lz + s)), 0.f);
+        box2[j] = ex * ex + ey * ey + ez * ez;
+        want[j] = (unsigned)cx <= (unsigned)cl_max && (unsigned)cy <= (unsigned)cl_max && (unsigned)cz <= (unsigned)cl_max && box2[j] <= reach2;
+        ckey[j] = ((sel3(mx, oo / 9) | sel3(my, (oo / 3) % 3) | sel3(mz, oo % 3)) << 4) | (unsigned)l;
+        if (want[j]) e[j] = __ldg(reinterpret_cast<const uint4*>(&a.table[grid_hash(ckey[j]) & a.tmask]));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      if (!want[j]) continue;
+      unsigned pos = grid_hash(ckey[j]) & a.tmask;
+      uint4 ent = e[j];
+      bool found = false;
+      for (;;) {
+        const unsigned long long cur = ((unsigned long long)ent.y << 32) | ent.x;
+        if (cur == ckey[j]) { found = true; break; }
+        if (cur == kGridEmpty) break;
+        pos = (pos + 1) & a.tmask;
+        ent = __ldg(reinterpret_cast<const uint4*>(&a.table[pos]));
+      }
+      if (!found) continue;
+      {
+        const float reach = sqrtf(__uint_as_float(T)) + slack;  // the bound may have tightened since the probe was issued
+        if (box2[j] > reach * reach) continue;
+      }
+      const int st = (int)ent.z, en = (int)ent.w;
+      scanned += en - st;
+      if (scanned > kDeferCandidates) {  // a lone thread would stall its warp: block-cooperative kernel (scans the block afresh)
+        a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, l);
+        return;
+      }
+      cnt = scan_cell(buf, cnt, T, q, a.sorted, st, en, k, cap);
+      if (cnt < 0) {  // ties (duplicate points) that a distance threshold cannot separate: cooperative kernel
+        a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, l);
+        return;
+      }
+    }
+  }
+  // 3. the k smallest of the buffered keys, ascending: tighten once more, then rank the survivors among themselves
+  T = tighten_threshold(buf, cnt, k, 2, T);
+  cnt = compact_below(buf, cnt, T);
+  int* row = a.nbr + (size_t)qi * k;
+  for (int j = 0; j < cnt; j++) {
+    const tkey ej = KNN_BUF(j);
+    int r = 0;
+    for (int m = 0; m < cnt; m++) r += KNN_BUF(m) < ej ? 1 : 0;
+    if (r < k) row[r] = key_index(ej);
+  }
+}
+#undef KNN_BUF
+#undef KNN_BUF_HI
+
+// ---- warp-level sorted top-k (k <= 64) for the block-cooperative kernel: rank r lives in lane r & 31, register r >> 5.
+// WIDE=false (k <= 32) keeps a single register set. ----
 struct WarpTopK {
   tkey e0, e1;
   tkey worst;  // entry of rank k-1, broadcast
@@ -529,12 +822,10 @@ __device__ __forceinline__ void topk_merge32(WarpTopK& t, int k, int lane, tkey 
 }
 
 // all 32 lanes call this with their candidate (valid=false for padding lanes)
-// `bound`: an upper bound on the k-th smallest key known from a previous (smaller) block -- candidates above it cannot be among
-// the k nearest and are dropped before they cost a merge
 template <bool WIDE>
-__device__ __forceinline__ void topk_offer(WarpTopK& t, int k, int lane, bool valid, float cd, int ci, tkey bound = kKeyInf) {
+__device__ __forceinline__ void topk_offer(WarpTopK& t, int k, int lane, bool valid, float cd, int ci) {
   const tkey c = make_key(cd, ci);
-  const bool pass = valid && c < t.worst && c <= bound;
+  const bool pass = valid && c < t.worst;
   unsigned m = __ballot_sync(0xffffffffu, pass);
   if (!WIDE && __popc(m) > 3) {  // many entrants: one sort-merge instead of one insertion each
     topk_merge32(t, k, lane, pass ? c : kKeyInf);
@@ -567,132 +858,10 @@ __device__ __forceinline__ void topk_offer(WarpTopK& t, int k, int lane, bool va
   }
 }
 
-__device__ __forceinline__ float topk_worst_d2(const WarpTopK& t) { return __uint_as_float((unsigned)(t.worst >> 32)); }
-__device__ __forceinline__ int key_index(tkey e) { return (int)(unsigned)(e & 0xffffffffULL); }
-
-__device__ __forceinline__ float knn_d2(float4 q, float4 t) {  // (dx*dx + dy*dy) + dz*dz, no contraction
-  float dx = __fsub_rn(t.x, q.x), dy = __fsub_rn(t.y, q.y), dz = __fsub_rn(t.z, q.z);
-  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-}
-
-// scan one contiguous run of the cell-sorted array (whole-cloud fallback), four loads in flight
+// scan one contiguous run of the sorted array; the 32-point batches are dealt round-robin to `nw` cooperating warps (warp `wi`
+// takes batches wi, wi+nw, ...), four loads in flight
 template <bool WIDE>
-__device__ __forceinline__ void scan_run(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int start, int count, tkey bound = kKeyInf) {
-  constexpr int U = 4;
-  for (int off = 0; off < count; off += 32 * U) {
-    float4 c[U];
-    bool valid[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      int j = off + u * 32 + lane;
-      valid[u] = j < count;
-      c[u] = valid[u] ? __ldg(&sorted[start + j]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++)
-      if (off + u * 32 < count) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w), bound);
-  }
-}
-
-__device__ __forceinline__ void probe_cell(const GridLevel& lv, unsigned tmask, int x, int y, int z, int& start, int& count) {
-  count = 0;
-  start = 0;
-  if (x < 0 || y < 0 || z < 0) return;  // no point lies below the bounding-box minimum
-  unsigned long long key = grid_key(x, y, z);
-  unsigned pos = grid_hash(key) & tmask;
-  for (;;) {
-    unsigned long long cur = __ldg(&lv.keys[pos]);
-    if (cur == key) { start = __ldg(&lv.start[pos]); count = __ldg(&lv.cnt[pos]); return; }
-    if (cur == kGridEmpty) return;
-    pos = (pos + 1) & tmask;
-  }
-}
-
-// scan the points of the (up to 32) cells probed by the lanes.  Cells are small (~5 points on the level that wins), so the
-// candidates of all cells are flattened into one index space (prefix sum of the counts across lanes) and consumed in
-// full 32-wide batches; each lane finds the cell of its candidate with a 5-step binary search over the lanes' prefix
-// values.  Four batches (loads) are kept in flight: a sparse query can own thousands of candidates and a single warp
-// is latency-bound.
-template <bool WIDE>
-__device__ __forceinline__ void scan_lane_cells(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int my_start, int my_count, tkey bound = kKeyInf) {
-  int incl = my_count;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  const int excl = incl - my_count;
-  constexpr int U = 4;
-  for (int base = 0; base < total; base += 32 * U) {
-    float4 c[U];
-    bool valid[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const int j = base + u * 32 + lane;
-      valid[u] = j < total;
-      c[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (base + u * 32 < total) {  // warp-uniform
-        int cell = 0;  // largest lane index whose exclusive prefix is <= j (runs of equal prefixes end at the non-empty cell)
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-          int e = __shfl_sync(0xffffffffu, excl, (cell + step) & 31);
-          if (e <= j) cell += step;
-        }
-        int st = __shfl_sync(0xffffffffu, my_start, cell);
-        int ex = __shfl_sync(0xffffffffu, excl, cell);
-        if (valid[u]) c[u] = __ldg(&sorted[st + (j - ex)]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (base + u * 32 < total) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w), bound);
-    }
-  }
-}
-
-// the same scans with the batches dealt round-robin to `nw` cooperating warps (warp `wi` takes batches wi, wi+nw, ...)
-template <bool WIDE>
-__device__ __forceinline__ void scan_lane_cells_strided(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int my_start, int my_count, int wi, int nw,
-                                                        tkey bound = kKeyInf) {
-  int incl = my_count;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  const int excl = incl - my_count;
-  constexpr int U = 4;
-  for (int base = wi * 32; base < total; base += 32 * U * nw) {
-    float4 c[U];
-    bool valid[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const int b0 = base + u * 32 * nw;
-      const int j = b0 + lane;
-      valid[u] = j < total;
-      c[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b0 < total) {
-        int cell = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-          int e = __shfl_sync(0xffffffffu, excl, (cell + step) & 31);
-          if (e <= j) cell += step;
-        }
-        int st = __shfl_sync(0xffffffffu, my_start, cell);
-        int ex = __shfl_sync(0xffffffffu, excl, cell);
-        if (valid[u]) c[u] = __ldg(&sorted[st + (j - ex)]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++)
-      if (base + u * 32 * nw < total) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w), bound);
-  }
-}
-
-template <bool WIDE>
-__device__ __forceinline__ void scan_run_strided(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int start, int count, int wi, int nw, tkey bound = kKeyInf) {
+__device__ __forceinline__ void scan_run_strided(WarpTopK& t, int k, int lane, float4 q, const float4* __restrict__ sorted, int start, int count, int wi, int nw) {
   constexpr int U = 4;
   for (int off = wi * 32; off < count; off += 32 * U * nw) {
     float4 c[U];
@@ -705,192 +874,68 @@ __device__ __forceinline__ void scan_run_strided(WarpTopK& t, int k, int lane, f
     }
 #pragma unroll
     for (int u = 0; u < U; u++)
-      if (off + u * 32 * nw < count) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w), bound);
+      if (off + u * 32 * nw < count) topk_offer<WIDE>(t, k, lane, valid[u], knn_d2(q, c[u]), __float_as_int(c[u].w));
   }
 }
 
-// Extension step.  The 3x3x3 block of a level held >= k points, but its k-th distance B exceeds the certificate radius s.  Every
-// true neighbour lies within B of q, and while B <= 2 s that ball is inside the 5x5x5 block around q's cell: merging the shell
-// cells (5^3 minus the 3^3 already merged) that intersect the ball completes the answer exactly.  On LiDAR surfaces that is a
-// handful of points, against the ~4x larger block of the next coarser level a restart would scan.
-template <bool WIDE>
-__device__ __forceinline__ bool extend_shell(WarpTopK& t, int k, int lane, float4 q, const GridGeom& g, float s, const GridLevel& lv, unsigned tmask, int3 c) {
-  const float B = sqrtf(topk_worst_d2(t));
-  if (!(B <= 2.f * s * 0.999f)) return false;  // (also rejects an unfilled list)
-  const float reach = B + 1e-3f * s;           // slack for the rounding of the cell boundaries
-  const float reach2 = reach * reach;
-  const float fx = q.x - g.minx, fy = q.y - g.miny, fz = q.z - g.minz;
-  for (int r = 0; r < 4; r++) {
-    const int idx = r * 32 + lane;
-    int st = 0, cn = 0;
-    if (idx < 125) {
-      const int dx = idx / 25 - 2, dy = (idx / 5) % 5 - 2, dz = idx % 5 - 2;
-      if (max(abs(dx), max(abs(dy), abs(dz))) == 2) {
-        const int cx = c.x + dx, cy = c.y + dy, cz = c.z + dz;
-        const float lx = cx * s, ly = cy * s, lz = cz * s;
-        const float ex = fmaxf(fmaxf(lx - fx, fx - (lx + s)), 0.f), ey = fmaxf(fmaxf(ly - fy, fy - (ly + s)), 0.f), ez = fmaxf(fmaxf(lz - fz, fz - (lz + s)), 0.f);
-        if (ex * ex + ey * ey + ez * ez <= reach2) probe_cell(lv, tmask, cx, cy, cz, st, cn);
-      }
-    }
-    if (__any_sync(0xffffffffu, cn > 0)) scan_lane_cells<WIDE>(t, k, lane, q, lv.sorted, st, cn);
-  }
-  return true;
-}
+constexpr int kKnnGridWarps = 8;  // warps per block of the cooperative kernel
 
-constexpr int kKnnGridWarps = 8;      // warps (queries) per block
-constexpr int kHeavyCandidates = 768; // blocks with more candidates than this go to the block-cooperative kernel
-// nearest-first order of the 3x3x3 block (index = 9*(dx+1) + 3*(dy+1) + (dz+1)): centre, 6 faces, 12 edges, 8 corners
-__constant__ unsigned char kBlockOrder[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25, 0, 2, 6, 8, 18, 20, 24, 26};
-
-// Persistent warps pull queries from a global counter (the cost of a query varies by >10x between dense and sparse
-// regions, and queries are visited in cell order, so static blocks would leave a long tail).
+// Block-cooperative continuation for the deferred queries: the 8 warps of a block split the candidates of one query -- the runs
+// of the 27 cells of its block at the recorded level, or the whole cloud -- each keeps its own sorted top-k, warp 0 merges the
+// eight lists through shared memory.  The block at that level contains the k nearest by construction (k_knn_search step 2).
 template <bool WIDE>
-__global__ void __launch_bounds__(kKnnGridWarps * 32, 4) k_knn_grid(GridArgs a, int force_bruteforce) {
-  const int lane = threadIdx.x & 31;
-  const int k = a.k;
-  GridGeom g = grid_geom(a.bbox_min, a.bbox_max);
-  // nearest-first cell order inside the 3x3x3 block: centre, faces, edges, corners
-  int dx = 0, dy = 0, dz = 0;
-  if (lane < 27) {
-    int o = kBlockOrder[lane];
-    dx = o / 9 - 1; dy = (o / 3) % 3 - 1; dz = o % 3 - 1;
-  }
+__global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_deferred(GridArgs a) {
+  __shared__ tkey se[kKnnGridWarps][64];
+  __shared__ int s_next;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int k = a.k, L = a.L;
+  const GridGeom g = grid_geom(a.bbox_min, a.bbox_max, L);
+  const int n_items = *a.defer_count;
   for (;;) {
-    int w = 0;
-    if (lane == 0) w = atomicAdd(a.query_cursor, 1);
-    w = __shfl_sync(0xffffffffu, w, 0);
-    if (w >= a.n) return;
-    // queries in the finest level's cell order: neighbouring warps touch the same cells
-    float4 q = __ldg(&a.lv[0].sorted[w]);
+    __syncthreads();
+    if (threadIdx.x == 0) s_next = atomicAdd(a.defer_cursor, 1);
+    __syncthreads();
+    const int h = s_next;
+    if (h >= n_items) return;
+    const int2 item = a.defer_queue[h];
+    const float4 q = __ldg(&a.sorted[item.x]);
     const int qi = __float_as_int(q.w);
     WarpTopK t;
     topk_reset(t);
-    bool done = false, deferred = false;
-    tkey bound = kKeyInf;  // k-th key of the last block that failed to certify: an upper bound on the true k-th key
-    if (!force_bruteforce) {
-      for (int l = 0; l < a.L && !done; l++) {
-        const float s = grid_cell_size(g, l, a.L);
-        if (bound != kKeyInf) {  // a level whose certificate radius is below the known lower bound s_prev cannot help; one that covers
-          const float need = sqrtf(__uint_as_float((unsigned)(bound >> 32)));  // the upper bound certifies for sure: skip in between
-          if (l + 1 < a.L && s * 0.999f < need && grid_cell_size(g, l + 1, a.L) * 0.999f <= need) continue;
-        }
-        const float inv_s = 1.0f / s;
-        const GridLevel lv = a.lv[l];
-        int3 c = grid_cell(g, inv_s, q.x, q.y, q.z);
-        int st = 0, cn = 0;
-        if (lane < 27) probe_cell(lv, a.tmask, c.x + dx, c.y + dy, c.z + dz, st, cn);
-        int total = cn;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-        // A surface sampled at density rho puts ~9 rho s^2 points in the block and ~pi rho s^2 within distance s, so the block
-        // can only certify k neighbours when it holds >~ 2.9 k points: below 2.5 k go straight to the coarser level.
-        if (total < k || (2 * total < 5 * k && l + 1 < a.L)) continue;
-        if (total > kHeavyCandidates) {  // a lone warp is latency-bound: hand big blocks to the block-cooperative kernel
-          if (lane == 0) a.heavy_queue[atomicAdd(a.heavy_count, 1)] = make_int2(w, l);
-          deferred = true;
-          break;
-        }
-        topk_reset(t);
-        scan_lane_cells<WIDE>(t, k, lane, q, lv.sorted, st, cn, bound);
-        const float r1 = s * 0.999f;
-        if (topk_worst_d2(t) <= r1 * r1) { done = true; break; }  // every point within s of q lies inside the 3x3x3 block
-        if (t.worst != kKeyInf) {
-          if (extend_shell<WIDE>(t, k, lane, q, g, s, lv, a.tmask, c)) { done = true; break; }
-          bound = t.worst;
+    if (item.y < L) {
+      const int l = item.y;
+      const int3 c0 = grid_cell0(g, q.x, q.y, q.z);
+      const int cl_max = g.cmax >> l;
+      int st = 0, en = 0;
+      if (lane < 27) {
+        const int cx = (c0.x >> l) + lane / 9 - 1, cy = (c0.y >> l) + (lane / 3) % 3 - 1, cz = (c0.z >> l) + lane % 3 - 1;
+        if ((unsigned)cx <= (unsigned)cl_max && (unsigned)cy <= (unsigned)cl_max && (unsigned)cz <= (unsigned)cl_max) {
+          if (!cell_range(a, (morton3(cx, cy, cz) << 4) | (unsigned)l, st, en)) st = en = 0;
         }
       }
+      for (int c = 0; c < 27; c++) {
+        const int s0 = __shfl_sync(0xffffffffu, st, c), e0 = __shfl_sync(0xffffffffu, en, c);
+        if (e0 > s0) scan_run_strided<WIDE>(t, k, lane, q, a.sorted, s0, e0 - s0, wid, kKnnGridWarps);
+      }
+    } else {
+      scan_run_strided<WIDE>(t, k, lane, q, a.sorted, 0, a.n, wid, kKnnGridWarps);
     }
-    if (deferred) continue;
-    if (!done) {  // no level could certify the answer (tiny cloud, far outlier): whole cloud, block-cooperative
-      if (lane == 0) a.heavy_queue[atomicAdd(a.heavy_count, 1)] = make_int2(w, a.L);
-      continue;
-    }
-    int* row = a.nbr + (size_t)qi * k;
-    if (lane < k) row[lane] = key_index(t.e0);
-    if (WIDE && 32 + lane < k) row[32 + lane] = key_index(t.e1);
-  }
-}
-
-// Block-cooperative continuation for the deferred queries: the 8 warps of a block split the candidates of one query
-// (warp j takes batches j, j+8, ...), each keeps its own sorted top-k, warp 0 merges the eight lists through shared
-// memory and applies the same certificate; a query that still fails moves to the next level, and past the coarsest
-// level the block scans the whole cloud.
-template <bool WIDE>
-__global__ void __launch_bounds__(kKnnGridWarps * 32) k_knn_grid_heavy(GridArgs a) {
-  __shared__ tkey se[kKnnGridWarps][64];
-  __shared__ int s_next;
-  __shared__ int s_done;
-  __shared__ tkey s_bound;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int k = a.k;
-  GridGeom g = grid_geom(a.bbox_min, a.bbox_max);
-  int dx = 0, dy = 0, dz = 0;
-  if (lane < 27) {
-    int o = kBlockOrder[lane];
-    dx = o / 9 - 1; dy = (o / 3) % 3 - 1; dz = o % 3 - 1;
-  }
-  const int n_heavy = *a.heavy_count;
-  for (;;) {
+    // merge the per-warp lists in warp 0
+    se[wid][lane] = t.e0;
+    se[wid][32 + lane] = t.e1;
     __syncthreads();
-    if (threadIdx.x == 0) s_next = atomicAdd(a.heavy_cursor, 1);
-    __syncthreads();
-    const int h = s_next;
-    if (h >= n_heavy) return;
-    const int2 item = a.heavy_queue[h];
-    float4 q = __ldg(&a.lv[0].sorted[item.x]);
-    const int qi = __float_as_int(q.w);
-    WarpTopK t;
-    tkey bound = kKeyInf;
-    for (int l = item.y; l <= a.L; l++) {
-      topk_reset(t);
-      float s = 0.f;
-      GridLevel lv = a.lv[0];
-      int3 c = make_int3(0, 0, 0);
-      if (l < a.L) {
-        s = grid_cell_size(g, l, a.L);
-        if (bound != kKeyInf) {
-          const float need = sqrtf(__uint_as_float((unsigned)(bound >> 32)));
-          if (l + 1 < a.L && s * 0.999f < need && grid_cell_size(g, l + 1, a.L) * 0.999f <= need) continue;  // identical in all warps
+    if (wid == 0) {
+      for (int ww = 1; ww < kKnnGridWarps; ww++) {
+        tkey e = se[ww][lane];
+        topk_offer<WIDE>(t, k, lane, lane < k, __uint_as_float((unsigned)(e >> 32)), key_index(e));
+        if (WIDE) {
+          e = se[ww][32 + lane];
+          topk_offer<WIDE>(t, k, lane, 32 + lane < k, __uint_as_float((unsigned)(e >> 32)), key_index(e));
         }
-        const float inv_s = 1.0f / s;
-        lv = a.lv[l];
-        c = grid_cell(g, inv_s, q.x, q.y, q.z);
-        int st = 0, cn = 0;
-        if (lane < 27) probe_cell(lv, a.tmask, c.x + dx, c.y + dy, c.z + dz, st, cn);
-        int total = cn;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-        if (total < k) continue;  // warp-uniform and identical in all warps
-        scan_lane_cells_strided<WIDE>(t, k, lane, q, lv.sorted, st, cn, wid, kKnnGridWarps, bound);
-      } else {
-        scan_run_strided<WIDE>(t, k, lane, q, a.lv[0].sorted, 0, a.n, wid, kKnnGridWarps, bound);
       }
-      // merge the per-warp lists in warp 0
-      se[wid][lane] = t.e0;
-      se[wid][32 + lane] = t.e1;
-      __syncthreads();
-      if (wid == 0) {
-        for (int ww = 1; ww < kKnnGridWarps; ww++) {
-          tkey e = se[ww][lane];
-          topk_offer<WIDE>(t, k, lane, lane < k, __uint_as_float((unsigned)(e >> 32)), key_index(e));
-          if (WIDE) {
-            e = se[ww][32 + lane];
-            topk_offer<WIDE>(t, k, lane, 32 + lane < k, __uint_as_float((unsigned)(e >> 32)), key_index(e));
-          }
-        }
-        const float r1 = s * 0.999f;
-        bool ok = (l == a.L) || (topk_worst_d2(t) <= r1 * r1);
-        if (!ok && t.worst != kKeyInf) ok = extend_shell<WIDE>(t, k, lane, q, g, s, lv, a.tmask, c);
-        if (ok) {
-          int* row = a.nbr + (size_t)qi * k;
-          if (lane < k) row[lane] = key_index(t.e0);
-          if (WIDE && 32 + lane < k) row[32 + lane] = key_index(t.e1);
-        }
-        if (lane == 0) { s_done = ok ? 1 : 0; s_bound = t.worst; }
-      }
-      __syncthreads();
-      if (s_done) break;
-      if (s_bound != kKeyInf) bound = s_bound;
+      int* row = a.nbr + (size_t)qi * k;
+      if (lane < k) row[lane] = key_index(t.e0);
+      if (WIDE && 32 + lane < k) row[32 + lane] = key_index(t.e1);
     }
   }
 }
@@ -931,67 +976,80 @@ size_t knn_grid_scratch_bytes(int n, int* levels_out, unsigned* table_size_out) 
   for (long m = 16384; m * 4 <= (long)n && L < kGridMaxLevels; m *= 4) L++;
   if (n < 4096) L = 6;
   unsigned T = 1024;
-  while (T < 2u * (unsigned)n) T <<= 1;
+  while (T < 4u * (unsigned)n) T <<= 1;
   if (levels_out) *levels_out = L;
   if (table_size_out) *table_size_out = T;
-  size_t per_level = (size_t)T * (8 + 4 + 4 + 4) + (size_t)n * (16 + 4);
-  return 4096 + (size_t)L * per_level + (size_t)n * 8;
+  const size_t sort_bytes = (sort_scratch_bytes(n, sort_num_passes(3 * (L + 1))) + 15) & ~(size_t)15;
+  return 4096 + (size_t)T * sizeof(CellEntry) + sort_bytes + (size_t)n * (8 + 8 + 4 + 4 + 16 + 8) + 256;
 }
 
-// scratch layout:  [0xFF-filled : bbox min (16 B) | keys of all levels]
-//                  [zero-filled : bbox max (16 B) | level cursors (64 B) | cnt, fill of all levels]
-//                  [uninitialised: start of all levels | sorted copies | pslot]
-cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned char* scratch, size_t scratch_bytes, int force_bruteforce, int blocks_per_sm_hint, int* launches,
+// scratch layout:  [0xFF-filled : bbox min (16 B) | cell table]
+//                  [zero-filled : bbox max (16 B) | counters (256 B) | sort scratch (digit histograms, tickets, look-back state)]
+//                  [uninitialised: Morton codes x2 | sort values x2 | sorted points | deferred-query queue]
+// q_begin/q_end: sorted positions whose neighbours are searched (whole cloud: 0, n); the build always covers the whole cloud.
+cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned char* scratch, size_t scratch_bytes, int force_bruteforce, int q_begin, int q_end, int* launches,
                             cudaStream_t stream) {
   int L;
   unsigned T;
   size_t need = knn_grid_scratch_bytes(n, &L, &T);
   if (scratch_bytes < need || (reinterpret_cast<uintptr_t>(scratch) & 15)) return cudaErrorInvalidValue;
+  if (q_end > n) q_end = n;
+  if (q_begin < 0) q_begin = 0;
+  const int key_bits = 3 * (L + 1);
+  const int passes = sort_num_passes(key_bits);
   GridArgs a;
-  a.pts = pts; a.n = n; a.k = k; a.L = L; a.tmask = T - 1; a.nbr = nbr;
+  a.pts = pts; a.n = n; a.k = k; a.L = L; a.tmask = T - 1; a.nbr = nbr; a.q_begin = q_begin; a.q_end = q_end;
   unsigned char* p = scratch;
   unsigned char* ff_begin = p;
   a.bbox_min = reinterpret_cast<unsigned*>(p); p += 16;
-  for (int l = 0; l < L; l++) { a.lv[l].keys = reinterpret_cast<unsigned long long*>(p); p += (size_t)T * 8; }
+  a.table = reinterpret_cast<CellEntry*>(p); p += (size_t)T * sizeof(CellEntry);
   const size_t ff_bytes = (size_t)(p - ff_begin);
   unsigned char* z_begin = p;
   a.bbox_max = reinterpret_cast<unsigned*>(p); p += 16;
-  a.level_cursor = reinterpret_cast<int*>(p); p += 64;
-  a.query_cursor = a.level_cursor + 15;
-  a.heavy_count = a.level_cursor + 14;
-  a.heavy_cursor = a.level_cursor + 13;
-  for (int l = 0; l < L; l++) {
-    a.lv[l].cnt = reinterpret_cast<int*>(p); p += (size_t)T * 4;
-    a.lv[l].fill = reinterpret_cast<int*>(p); p += (size_t)T * 4;
-  }
+  int* counters = reinterpret_cast<int*>(p); p += 256;
+  a.level_hist = counters;  // [0 .. kGridMaxLevels + 1]
+  a.l_min = counters + 16;
+  a.done_blocks = reinterpret_cast<unsigned*>(counters + 17);
+  a.defer_count = counters + 18;
+  a.defer_cursor = counters + 19;
+  unsigned char* sort_scratch = p;
+  p += (sort_scratch_bytes(n, passes) + 15) & ~(size_t)15;
   const size_t z_bytes = (size_t)(p - z_begin);
-  for (int l = 0; l < L; l++) { a.lv[l].start = reinterpret_cast<int*>(p); p += (size_t)T * 4; }
-  for (int l = 0; l < L; l++) { a.lv[l].sorted = reinterpret_cast<float4*>(p); p += (size_t)n * 16; }
-  for (int l = 0; l < L; l++) { a.lv[l].pslot = reinterpret_cast<int*>(p); p += (size_t)n * 4; }
+  unsigned long long* codes0 = reinterpret_cast<unsigned long long*>(p); p += (size_t)n * 8;
+  unsigned long long* codes1 = reinterpret_cast<unsigned long long*>(p); p += (size_t)n * 8;
+  unsigned* vals0 = reinterpret_cast<unsigned*>(p); p += (size_t)n * 4;
+  unsigned* vals1 = reinterpret_cast<unsigned*>(p); p += (size_t)n * 4;
   p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
-  a.heavy_queue = reinterpret_cast<int2*>(p); p += (size_t)n * 8;
+  a.sorted = reinterpret_cast<float4*>(p); p += (size_t)n * 16;
+  a.defer_queue = reinterpret_cast<int2*>(p); p += (size_t)n * 8;
+  a.codes = codes0;
   cudaError_t e;
   if ((e = cudaMemsetAsync(ff_begin, 0xFF, ff_bytes, stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(z_begin, 0, z_bytes, stream)) != cudaSuccess) return e;
+  int nl = 0;
   const int nb = (n + 255) / 256;
   k_grid_bbox<<<nb < 592 ? nb : 592, 256, 0, stream>>>(pts, n, a.bbox_min, a.bbox_max);
-  k_grid_count<<<dim3(nb, L), 256, 0, stream>>>(a);
-  k_grid_alloc<<<dim3((T + 255) / 256, L), 256, 0, stream>>>(a);
-  k_grid_scatter<<<dim3(nb, L), 256, 0, stream>>>(a);
-  int qblocks = (n + kKnnGridWarps - 1) / kKnnGridWarps;
-  // persistent warps pull queries from a counter; 4 blocks (32 warps) per SM by default, 2 when many handles share the GPU
-  // (leaves room for other streams' kernels on every SM: +3..6 % aggregate throughput, slower alone)
-  const int blocks_per_sm = (blocks_per_sm_hint >= 1 && blocks_per_sm_hint <= 8) ? blocks_per_sm_hint : 4;
-  if (qblocks > 148 * blocks_per_sm) qblocks = 148 * blocks_per_sm;  // persistent: queries pulled from a counter
-  int hblocks = qblocks < 148 * 4 ? qblocks : 148 * 4;
-  if (k <= 32) {
-    k_knn_grid<false><<<qblocks, kKnnGridWarps * 32, 0, stream>>>(a, force_bruteforce);
-    k_knn_grid_heavy<false><<<hblocks, kKnnGridWarps * 32, 0, stream>>>(a);
-  } else {
-    k_knn_grid<true><<<qblocks, kKnnGridWarps * 32, 0, stream>>>(a, force_bruteforce);
-    k_knn_grid_heavy<true><<<hblocks, kKnnGridWarps * 32, 0, stream>>>(a);
+  k_grid_codes<<<nb < 1184 ? nb : 1184, kSortThreads, 0, stream>>>(a, passes, reinterpret_cast<unsigned*>(sort_scratch));
+  nl += 2;
+  if ((e = launch_sort_pairs<unsigned long long>(codes0, vals0, codes1, vals1, n, key_bits, sort_scratch, true, pts, a.sorted, &nl, stream)) != cudaSuccess) return e;
+  a.codes = (passes & 1) ? codes1 : codes0;
+  k_grid_levels<<<nb < 592 ? nb : 592, 256, 0, stream>>>(a);
+  k_grid_table<<<dim3(nb, L), 256, 0, stream>>>(a);
+  nl += 2;
+  const int nq = q_end > q_begin ? q_end - q_begin : 0;
+  if (nq > 0) {
+    // candidate buffer per thread: the ~3k-point window of step 1 must fit, and the points within the bound of step 2 should
+    const int cap = k <= 20 ? 64 : (k <= 32 ? 104 : 200);
+    const size_t smem = (size_t)cap * kSearchThreads * sizeof(tkey);
+    if ((e = cudaFuncSetAttribute(k_knn_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)200 * kSearchThreads * sizeof(tkey)))) != cudaSuccess) return e;
+    k_knn_search<<<(nq + kSearchThreads - 1) / kSearchThreads, kSearchThreads, smem, stream>>>(a, cap, force_bruteforce);
+    int hblocks = (nq + kKnnGridWarps - 1) / kKnnGridWarps;
+    if (hblocks > 148 * 4) hblocks = 148 * 4;  // persistent: items pulled from a counter
+    if (k <= 32) k_knn_deferred<false><<<hblocks, kKnnGridWarps * 32, 0, stream>>>(a);
+    else k_knn_deferred<true><<<hblocks, kKnnGridWarps * 32, 0, stream>>>(a);
+    nl += 2;
   }
-  if (launches) *launches = 6;
+  if (launches) *launches = nl;
   return cudaGetLastError();
 }
 
@@ -1000,8 +1058,9 @@ cudaError_t launch_covariance_knn(const float4* pts, const int* nbr, int n, int 
   return cudaGetLastError();
 }
 
-cudaError_t launch_covariance_rbf(const float4* pts, int n, float exp_factor, float max_dist, int method, float4* covA, float2* covB, cudaStream_t stream) {
-  k_covariance_rbf<<<(n + 127) / 128, 128, 0, stream>>>(pts, n, exp_factor, max_dist, method, covA, covB);
+cudaError_t launch_covariance_rbf(const float4* pts, int n, float exp_factor, float max_dist, int method, float* boxes, float4* covA, float2* covB, cudaStream_t stream) {
+  k_rbf_block_boxes<<<(n + kRbfBlock - 1) / kRbfBlock, 128, 0, stream>>>(pts, n, boxes);
+  k_covariance_rbf<<<(n + 127) / 128, 128, 0, stream>>>(pts, n, exp_factor, max_dist, method, boxes, covA, covB);
   return cudaGetLastError();
 }
 

@@ -266,9 +266,27 @@ ORC_API void orc_covariances(const float* pts, int n, int k, const int* nbr, flo
  *     A padding point inside max_dist of the query adds its weight to sum_w (and nothing else, it sits at the origin).
  *     float throughout, every a*b+c two roundings (the CUDA path's stage-1 unit is compiled --fmad=false and spells the same
  *     sequence).  The weight: the reference calls CUDA's expf (a 2-ulp function that no CPU libm reproduces bit for bit); both
- *     sides here evaluate exp in double and round once, i.e. the correctly rounded float -- within the error bound of the
- *     reference's own function.  cov9: column-major 3x3 per point like every other covariance of the oracle.
+ *     sides here evaluate the same exp built from IEEE single operations (exp_det, Cephes' expf: about 1 ulp) -- within the
+ *     error class of the reference's own function.  cov9: column-major 3x3 per point like every other covariance of the oracle.
  * ---------------------------------------------------------------------------------------------------------- */
+/* exp(x), x <= 0, from IEEE single operations only (Cephes' expf), the same sequence the CUDA path spells */
+static float exp_det(float x) {
+  if (x < -87.0f) return 0.0f;
+  const float n = rintf(x * 1.44269504088896341f);
+  float r = fmaf(n, -0.693359375f, x);
+  r = fmaf(n, 2.12194440e-4f, r);
+  float p = 1.9875691500e-4f;
+  p = fmaf(p, r, 1.3981999507e-3f);
+  p = fmaf(p, r, 8.3334519073e-3f);
+  p = fmaf(p, r, 4.1665795894e-2f);
+  p = fmaf(p, r, 1.6666665459e-1f);
+  p = fmaf(p, r, 5.0000001201e-1f);
+  p = fmaf(p, r * r, r) + 1.0f;
+  union { int i; float f; } sc;
+  sc.i = ((int)n + 127) << 23;
+  return p * sc.f;
+}
+
 #define ORC_RBF_BLOCK 512
 ORC_API void orc_covariances_rbf(const float* pts, int n, float kernel_width, float max_dist, float* cov9) {
   const float max_dist_sq = max_dist * max_dist;
@@ -286,7 +304,7 @@ ORC_API void orc_covariances_rbf(const float* pts, int n, float kernel_width, fl
         const float dx = x[0] - p[0], dy = x[1] - p[1], dz = x[2] - p[2];
         const float sq = (dx * dx + dy * dy) + dz * dz;
         if (sq > max_dist_sq) continue;
-        const float w = (float)exp((double)(-kernel_width * sq));
+        const float w = exp_det(-kernel_width * sq);
         psw += w;
         const float wp[3] = {w * p[0], w * p[1], w * p[2]};
         for (int d = 0; d < 3; d++) pm[d] += wp[d];

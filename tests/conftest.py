@@ -48,8 +48,12 @@ def pose_error(T_ref, T):
     """(translation error [m], rotation error [rad]) of T against T_ref -- gicp_test.cpp:75-80."""
     d = np.linalg.inv(np.asarray(T_ref, dtype=np.float64)) @ np.asarray(T, dtype=np.float64)
     t = float(np.linalg.norm(d[:3, 3]))
-    c = (np.trace(d[:3, :3]) - 1.0) / 2.0
-    return t, float(np.arccos(np.clip(c, -1.0, 1.0)))
+    # angle from sin and cos (atan2): arccos of the trace alone turns a 1e-7 non-orthonormality of a float32 pose matrix
+    # (pcl::Registration keeps Matrix4f) into sqrt(2e-7) = 4e-4 rad
+    R = d[:3, :3]
+    s = 0.5 * np.linalg.norm([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    c = (np.trace(R) - 1.0) / 2.0
+    return t, float(np.arctan2(s, c))
 
 
 def random_pose(rng, max_angle, max_trans):

@@ -32,10 +32,11 @@ def test_ndt_voxelmap_matches_oracle(pair02, res):
     coords, ids = c.get_voxel_buckets()
     assert np.array_equal(ids, vm.bucket_id) and np.array_equal(coords, vm.bucket_coord)
     assert np.array_equal(c.get_voxel_num_points(), vm.vox_n)
-    assert np.abs(c.get_voxel_means() - vm.vox_mean).max() < 1e-5
-    err = np.abs(c.get_voxel_covs() - sym(vm.vox_cov)).max(axis=1)
-    # MIN_EIG rebuilds V diag(max(ev,1e-3)) V^-1: few-point voxels are rank deficient, their eigenvectors are ill-conditioned
-    assert np.percentile(err, 95) < 1e-5 and err.max() < 5e-2, (np.percentile(err, 95), err.max())
+    # the points of a voxel are added in index order in double on both sides and the regulariser is the same restated eigen-solver:
+    # bit for bit, including the rank-deficient few-point voxels where the closed-form solver amplifies any input difference
+    assert np.array_equal(c.get_voxel_means(), vm.vox_mean)
+    bad = np.flatnonzero((c.get_voxel_covs() != sym(vm.vox_cov).astype(np.float32)).any(axis=1))
+    assert len(bad) <= 1, (len(bad), np.abs(c.get_voxel_covs() - sym(vm.vox_cov)).max())  # (one double-rounding tie of the trig step allowed)
     w = np.linalg.eigvalsh(c.get_voxel_covs().reshape(-1, 3, 3).astype(np.float64))
     assert w.min() > 0.99e-3  # eigenvalues clamped at 1e-3 (covariance_regularization.cu:84-101)
     c.close()
