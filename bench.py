@@ -113,7 +113,34 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------------------------------------- CPU arm
-_CPU_THREADS = None
+def numa_cpus(node):
+    """One hardware thread per physical core of a NUMA node (sysfs), or None."""
+    try:
+        txt = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        cpus = []
+        for part in txt.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        seen, out = set(), []
+        for c in cpus:
+            try:
+                sib = open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c).read().strip()
+            except OSError:
+                sib = str(c)
+            if sib not in seen:
+                seen.add(sib)
+                out.append(c)
+        return out or None
+    except (OSError, ValueError):
+        return None
+
+
+def cpu_thread_set():
+    """The CPU arm's threads: the physical cores of NUMA node 0 (capped at 32: OpenMP over ~17k points stops scaling there), fixed
+    and pinned, so that two runs on two boxes of the same class measure the same thing."""
+    allowed = sorted(os.sched_getaffinity(0))
+    cpus = [c for c in (numa_cpus(0) or allowed) if c in allowed] or allowed
+    return cpus[:32]
 
 
 def cpu_one_registration(w, offs, threads):
@@ -127,64 +154,224 @@ def cpu_one_registration(w, offs, threads):
     return O.align_f64(tgt, tc, src, sc, res=w["res"], offs=offs, threads=threads)
 
 
-def cpu_best_threads(w, offs):
-    """'All the host threads it can use': OpenMP over ~17k points stops scaling (and degrades) well before 128 threads, so
-    pick the fastest of a few thread counts once and use it for the timed sample."""
-    global _CPU_THREADS
-    if _CPU_THREADS is None:
-        ncpu = os.cpu_count() or 1
-        best = None
-        for t in sorted({min(ncpu, c) for c in (8, 16, 32, 64)}):
-            cpu_one_registration(w, offs, t)
-            t0 = time.perf_counter()
-            cpu_one_registration(w, offs, t)
-            dt = time.perf_counter() - t0
-            if best is None or dt < best[0]:
-                best = (dt, t)
-            elif dt > 1.5 * best[0]:
-                break  # past the scaling knee: more threads only add barrier cost
-        _CPU_THREADS = best[1]
-    return _CPU_THREADS
-
-
-def cpu_registration_loop(w, min_seconds, min_regs, max_regs):
-    """The reference's CPU implementation of this path (FastVGICP, OpenMP) restated in oracle/: per registration
-    calculate_covariances(target), calculate_covariances(source) (kd-tree kNN, k=20, PLANE), voxel map, LM align."""
+def run_reference_arm(args, w, rank, world):
+    """--impl reference: the reference's CPU implementation of this path (OpenMP FastVGICP, restated in oracle/ because the
+    reference cannot be compiled here: per registration calculate_covariances(target), calculate_covariances(source) (kd-tree
+    kNN, k=20, PLANE), voxel map, LM align) on a fixed, pinned set of host cores; rank 0 only.  A step is a bounded sample of
+    `regs_per_step` registrations (so that even a short --steps run times >= 30 of them); value = 1 / median registration time."""
+    if rank != 0:
+        return
+    cpus = cpu_thread_set()
+    # the OpenMP runtime reads these when the oracle library loads (first use below)
+    os.environ.setdefault("OMP_PROC_BIND", "true")
+    os.environ["OMP_PLACES"] = ",".join("{%d}" % c for c in cpus)
+    os.environ["OMP_NUM_THREADS"] = str(len(cpus))
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+    try:
+        os.sched_setaffinity(0, cpus)
+    except OSError:
+        pass
     import oracle as O
 
     offs = O.offsets(getattr(O, w["method"]))
-    threads = cpu_best_threads(w, offs)
+    threads = len(cpus)
+    per_step = max(1, -(-30 // max(args.steps, 1)))
+    for _ in range(max(args.warmup, 3)):
+        cpu_one_registration(w, offs, threads)
     times = []
-    t_end = time.perf_counter() + min_seconds
-    T = None
-    while (len(times) < min_regs or time.perf_counter() < t_end) and len(times) < max_regs:
+    for _ in range(args.steps * per_step):
         t0 = time.perf_counter()
-        r = cpu_one_registration(w, offs, threads)
+        cpu_one_registration(w, offs, threads)
         times.append(time.perf_counter() - t0)
-        T = r.T
-    return times, T, threads
-
-
-def run_reference_arm(args, w, rank, world):
-    """--impl reference: times the CPU implementation on the host cores (rank 0 only)."""
-    if rank != 0:
-        return
-    for _ in range(args.warmup):
-        cpu_registration_loop(w, 0.0, 1, 1)
-    times, _, threads = cpu_registration_loop(w, 0.0, args.steps, args.steps)
-    total = float(np.sum(times))
-    value = len(times) / total
+    med = float(np.median(times))
+    value = 1.0 / med
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": w["data"],
-        "config": {"workload": w["name"], "protocol": "align.cpp 100times (covariances recomputed every registration)", "step": "one registration",
-                   "host_cores": os.cpu_count()},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1e3 * med * per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": w["data"],
+        "config": {"workload": w["name"], "protocol": "align.cpp 100times (covariances recomputed every registration)", "step": "%d sequential registrations" % per_step,
+                   "registrations_timed": len(times), "statistic": "1 / median registration time", "mean_ms": 1e3 * float(np.mean(times)), "min_ms": 1e3 * float(np.min(times)),
+                   "host_cores": os.cpu_count(), "pinned_cpus": "%d-%d (%d threads, one per physical core of NUMA node 0)" % (cpus[0], cpus[-1], threads)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d full registrations, restated OpenMP FastVGICP in double (reference not buildable here: no Eigen/PCL); fastest of 8/16/32/64 threads" % len(times)},
+                         "sample": "%d full registrations (median), restated OpenMP FastVGICP in double (reference not buildable here: no Eigen/PCL), %d pinned threads" % (len(times), threads)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ host placement
+def gpu_numa_node(torch, local_rank):
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        return node if node >= 0 else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def pin_rank_threads(torch, local_rank, world):
+    """Keep this rank's host threads (one per registration stream) on cores of its GPU's NUMA node, an own slice per rank: with 8
+    ranks x 8 spinning threads on two sockets the scheduler otherwise migrates them across nodes (SCALE_r01: e2e efficiency 0.81)."""
+    node = gpu_numa_node(torch, local_rank)
+    if node is None:
+        return None
+    try:
+        txt = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        cpus = []
+        for part in txt.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        n_gpus = torch.cuda.device_count()
+        same = [g for g in range(n_gpus) if gpu_numa_node(torch, g) == node] or [local_rank]
+        if world > 1 and len(same) > 1 and local_rank in same:
+            j, m = same.index(local_rank), len(same)
+            phys = len(cpus) // 2 if len(cpus) >= 2 * m else len(cpus)  # cpulist = physical cores then their hyper-thread siblings
+            per = max(phys // m, 1)
+            mine = cpus[j * per:(j + 1) * per]
+            if phys < len(cpus):
+                mine = mine + cpus[phys + j * per:phys + (j + 1) * per]
+            cpus = mine or cpus
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": "%d..%d (%d)" % (cpus[0], cpus[-1], len(cpus))}
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def source_hash():
+    """Hash of the CUDA sources: profiles/traffic.json (ncu DRAM bytes per launch) is only quoted while it matches."""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "fast_gicp_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".hpp")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+# --------------------------------------------------------------------------------------------- C4 (1M-point pair)
+def c4_record(torch, dev, local_rank, rank, world, peak_gbs, note):
+    """BASELINE config 4: synthetic 1M-pt pair, res 0.5.  One GPU: stage times and the evaluation kernel against the HBM roofline
+    (DIRECT1 = the bandwidth-bound configuration, DIRECT27 = the issue-bound one).  Several GPUs: the same registration with the
+    source sharded over the ranks -- stage 1 (k-NN queries + covariances, exchanged by peer stores) and stage 3 (evaluation, 28 sums
+    exchanged inside the kernel over NVLink peer memory) -- against the unsharded one measured in the same run."""
+    from fast_gicp_b200 import distributed as D
+    from fast_gicp_b200.core import REG_PLANE, Core, pose_from_c
+    from fast_gicp_b200.synthetic import kitti_like_pair
+
+    tgt, src, _ = kitti_like_pair(beams=128, az_steps=8192, seed=44, pose=(0.5, 0.0, 1.0), downsample=0.0, max_points=1_000_000)
+    n_t, n_s = len(tgt), len(src)
+    d_t, d_s = torch.from_numpy(tgt).to(dev), torch.from_numpy(src).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def registration(c, timed=True):
+        st = torch.cuda.ExternalStream(c.stream(), device=dev)
+        flush.zero_()
+        torch.cuda.synchronize()
+        D.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        c.set_cloud_device("target", d_t.data_ptr(), n_t, 12)
+        c.find_target_neighbors(20)
+        c.calculate_target_covariances(REG_PLANE)
+        c.create_target_voxelmap()
+        c.set_cloud_device("source", d_s.data_ptr(), n_s, 12)
+        c.find_source_neighbors(20)
+        c.calculate_source_covariances(REG_PLANE)
+        r = c.align()
+        b.record(st)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b), r
+
+    def evaluation_ms(c, reps=10):
+        st = torch.cuda.ExternalStream(c.stream(), device=dev)
+        T = np.eye(4)
+        c.linearize(T)
+        torch.cuda.synchronize()
+        D.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for _ in range(reps):
+            out = c.linearize(T)
+        b.record(st)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps, out
+
+    rec = {"workload": "C4: synthetic 1M-pt pair (seeds 44/45), res 0.5, k=20 PLANE, LM defaults", "n_target": n_t, "n_source": n_s}
+    c = Core(local_rank)
+    c.set_resolution(0.5)
+    out = {}
+    for method in ("DIRECT27", "DIRECT1"):
+        c.set_neighbor_search_method(method)
+        for _ in range(2):
+            registration(c)
+        ts = [registration(c) for _ in range(3)]
+        ms_reg = float(np.median([t for t, _ in ts]))
+        res = ts[-1][1]
+        ms_eval, (e_full, H_full, b_full) = evaluation_ms(c)
+        c.set_profiling(True)
+        for _ in range(5):
+            c.linearize(np.eye(4))
+        prof = c.get_profile()
+        c.set_profiling(False)
+        kern_ms = prof["linearize"][0] / max(prof["linearize"][1], 1)
+        V, B = c.num_voxels(), c.num_buckets()
+        alg = 52.0 * n_s + 52.0 * V + 16.0 * B
+        ms_reg, ms_eval, kern_ms = D.max_over_ranks([ms_reg, ms_eval, kern_ms], device=dev)
+        out[method] = {"ms_per_registration": ms_reg, "ms_per_evaluation_host_driven": ms_eval, "evaluation_kernel_ms": kern_ms, "num_voxels": V, "num_buckets": B,
+                       "iterations": int(res.nr_iterations) + 1, "evaluations": int(res.n_linearize + res.n_compute_error), "converged": bool(res.converged),
+                       "roofline": {"bound": "hbm", "kernel": "k_linearize<%s> (one LM evaluation of 1M source points)" % method, "algorithmic_bytes_per_launch": alg,
+                                    "achieved": alg / (kern_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": alg / (kern_ms * 1e-3) / 1e9 / peak_gbs},
+                       "_unsharded": (e_full, H_full, b_full, pose_from_c(res.T))}
+        note("c4 %s: %.3f ms/registration, evaluation kernel %.1f us" % (method, ms_reg, 1e3 * kern_ms))
+    # stage times of one registration (CUDA events around every launch)
+    c.set_neighbor_search_method("DIRECT27")
+    c.set_profiling(True)
+    registration(c)
+    prof = c.get_profile()
+    c.set_profiling(False)
+    rec["stage_ms_direct27"] = {k: v[0] for k, v in prof.items() if v[1]}
+    if world > 1:
+        sh = {}
+        c2 = Core(local_rank)
+        c2.set_resolution(0.5)
+        lo, hi = D.setup_source_sharding(c2, n_s, max_points=max(n_s, n_t))
+        for method in ("DIRECT27", "DIRECT1"):
+            c2.set_neighbor_search_method(method)
+            for _ in range(2):
+                registration(c2)
+            ts = [registration(c2) for _ in range(3)]
+            ms_reg = float(np.median([t for t, _ in ts]))
+            res = ts[-1][1]
+            ms_eval, (e_sh, H_sh, b_sh) = evaluation_ms(c2)
+            ms_reg, ms_eval = D.max_over_ranks([ms_reg, ms_eval], device=dev)
+            e_full, H_full, b_full, T_full = out[method]["_unsharded"]
+            T_sh = pose_from_c(res.T)
+            sums = D.max_over_ranks([float(H_sh.sum()), -float(H_sh.sum()), float(T_sh.sum()), -float(T_sh.sum())], device=dev)
+            sh[method] = {"ms_per_registration": ms_reg, "ms_per_evaluation_host_driven": ms_eval,
+                          "speedup_vs_1": out[method]["ms_per_registration"] / ms_reg, "strong_scaling_efficiency": out[method]["ms_per_registration"] / ms_reg / world,
+                          "evaluation_speedup_vs_1": out[method]["ms_per_evaluation_host_driven"] / ms_eval,
+                          "H_rel_diff_vs_unsharded": float(np.abs(H_sh - H_full).max() / np.abs(H_full).max()),
+                          "pose_abs_diff_vs_unsharded": float(np.abs(T_sh - T_full).max()),
+                          "ranks_bit_identical": bool(sums[0] == -sums[1] and sums[2] == -sums[3]), "iterations": int(res.nr_iterations) + 1,
+                          "converged": bool(res.converged)}
+            note("c4 sharded x%d %s: %.3f ms/registration (x%.2f)" % (world, method, ms_reg, sh[method]["speedup_vs_1"]))
+        err = int(D.max_over_ranks([float(c2.comm_error())], device=dev)[0])
+        D.barrier()
+        c2.comm_shutdown()
+        c2.close()
+        rec["sharded"] = dict(sh, n_gpus=world, comm_error=err, source_slice_of_rank0=[int(lo), int(hi)],
+                              what="stage 1 (k-NN queries + covariances: peer stores into every rank's arrays) and stage 3 (evaluation: 28 sums per evaluation exchanged inside "
+                                   "the kernel through NVLink peer mailboxes) sharded; k-NN grid build and voxel map replicated")
+    for m in out.values():
+        m.pop("_unsharded")
+    rec.update(out)
+    c.close()
+    return rec
 
 
 # -------------------------------------------------------------------------------------------------------- GPU arm
@@ -206,10 +393,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--streams", type=int, default=0,
-                    help="concurrent registration streams per GPU (host thread + handle each); default 16, or 8 when more than 2 ranks share the host "
-                         "(every stream's thread spins on its completion word)")
+    ap.add_argument("--streams", type=int, default=8,
+                    help="concurrent registration streams per GPU (host thread + handle each); the same at every N (8 reach 98 %% of the 16-stream rate and "
+                         "leave the host cores of a NUMA node to the ranks that share it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 1M-point sub-record (config 4: evaluation roofline at N=1, sharded registration at N>1)")
     ap.add_argument("--e2e-impl", default="class", choices=["class", "batch"],
                     help="end-to-end arm: the FastVGICPCuda class from S Python threads (default, verified), or one vgicp_batch_register C call per timed region "
                          "(include/vgicp_batch_b200.h; not yet verified on hardware)")
@@ -239,6 +427,7 @@ def main():
     from fast_gicp_b200.core import REG_PLANE, Core, pose_from_c
 
     D.init("nccl", dev)  # one rank per GPU; used for the barrier and the max-over-ranks of the device time only
+    placement = pin_rank_threads(torch, local_rank, world)
 
     def barrier():
         D.barrier(cuda=True)
@@ -246,7 +435,7 @@ def main():
     tgt, src = w["target"], w["source"]
     n_t, n_s = len(tgt), len(src)
     K, W = args.steps, args.warmup
-    S = args.streams if args.streams > 0 else (16 if int(os.environ.get("WORLD_SIZE", "1")) <= 2 else 8)
+    S = max(args.streams, 1)
     _t0 = time.perf_counter()
 
     def note(msg):
@@ -447,16 +636,28 @@ def main():
     n_prof = min(K, 20)
     per_kernel = {k: {"ms_per_step": v[0] / n_prof, "launches_per_step": v[1] / n_prof} for k, v in prof.items() if v[1]}
 
-    if rank != 0:
-        D.finalize()
-        return
-
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak_gbs, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
     V, B = core.num_voxels(), core.num_buckets()
+    # ---- config 4 (all ranks take part: sharded over the ranks when there are several)
+    c4 = None
+    if args.workload == "c2" and not args.no_c4:
+        for c_ in cores[1:]:
+            c_.close()
+        del pool_t, pool_s, flush
+        torch.cuda.empty_cache()
+        try:
+            c4 = c4_record(torch, dev, local_rank, rank, world, peak_gbs, note)
+        except Exception as e:  # noqa: BLE001
+            c4 = {"error": repr(e)}
+        note("c4 record done")
+
+    if rank != 0:
+        D.finalize()
+        return
     # algorithmic bytes per launch, SURVEY.md 8(d)
     if ndt:
         METRIC_NAME = "registrations/sec (NDT D2D, KITTI-shaped pairs)"
@@ -482,12 +683,13 @@ def main():
         avg_ms = ms / max(launches_g, 1e-9)
         ab = alg_bytes[cats[0]]
         ach = ab / (avg_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = None  # ncu dram__bytes per launch, written by scripts/make_traffic.sh; quoted only while the kernels are the ones it measured
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             vals = [tj[c] for c in cats if c in tj]
-            traffic = float(np.mean(vals)) if vals else None
+            if tj.get("source_hash") == source_hash() and vals:
+                traffic = float(np.mean(vals))
         return {"bound": "hbm", "kernel": gname, "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": ab, "kernel_share_of_step": ms / total_kernel_ms}
 
@@ -531,7 +733,7 @@ def main():
         "single_stream": {"ms_per_registration": float(np.mean(lat)), "registrations_per_s": 1e3 / float(np.mean(lat)),
                           "e2e_ms_per_registration": float(np.mean(lat_e2e)), "e2e_registrations_per_s": 1e3 / float(np.mean(lat_e2e)),
                           "l2": "flushed between registrations (256 MiB memset)", "protocol": "sequential, as src/align.cpp:72-81"},
-        "wall_ms_per_step": 1e3 * wall_s / K,
+        "wall_ms_per_step": 1e3 * wall_s / K, "host_placement": placement, "c4": c4,
         "pose_check": {"translation": [float(x) for x in T_val[:3, 3]], "e2e_vs_resident_max_abs": float(np.abs(np.asarray(T_e2e, dtype=np.float64) - T_val).max())},
     }
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)

@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = [
     "vgicp_set_source_cloud_device", "vgicp_set_target_cloud_device", "vgicp_set_profiling", "vgicp_get_profile", "vgicp_profile_category_name",
     "vgicp_set_knn_mode", "vgicp_set_voxel_index", "vgicp_set_speculation", "vgicp_register", "vgicp_set_align_mode", "vgicp_get_fitness_score", "vgicp_set_execution_hint", "vgicp_set_problem", "vgicp_ndt_create_voxelmaps",
     "vgicp_comm_export", "vgicp_comm_init", "vgicp_comm_shutdown", "vgicp_comm_error", "vgicp_set_source_shard", "vgicp_clear_source_shard",
+    "vgicp_comm_export_arena", "vgicp_comm_init_arena", "vgicp_set_stage1_sharding",
 ]
 PROF_NUM_CATEGORIES = 7
 
@@ -138,6 +139,9 @@ def load_library():
         "vgicp_comm_error": [hp, ip],
         "vgicp_set_source_shard": [hp, C.c_size_t, C.c_size_t],
         "vgicp_clear_source_shard": [hp],
+        "vgicp_comm_export_arena": [hp, C.c_size_t, C.c_void_p],
+        "vgicp_comm_init_arena": [hp, C.c_void_p],
+        "vgicp_set_stage1_sharding": [hp, C.c_int],
         "vgicp_register": [hp, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, dp, C.POINTER(LsqParams), C.POINTER(AlignResult)],
         "vgicp_get_profile": [hp, dp, C.POINTER(C.c_uint64), C.c_int],
     }
@@ -457,6 +461,20 @@ class Core:
         assert len(blob) == 64 * nranks
         arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
         self._check(self._lib.vgicp_comm_init(self._h, int(rank), int(nranks), arr))
+
+    def comm_export_arena(self, max_points):
+        """Stage-1 sharding: allocate the exchange arena (covariances of both clouds, up to max_points each) and return its IPC handle."""
+        buf = (C.c_ubyte * 64)()
+        self._check(self._lib.vgicp_comm_export_arena(self._h, int(max_points), buf))
+        return bytes(buf)
+
+    def comm_init_arena(self, all_handles):
+        blob = b"".join(all_handles)
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self._lib.vgicp_comm_init_arena(self._h, arr))
+
+    def set_stage1_sharding(self, enable):
+        self._check(self._lib.vgicp_set_stage1_sharding(self._h, int(bool(enable))))
 
     def comm_shutdown(self):
         self._check(self._lib.vgicp_comm_shutdown(self._h))

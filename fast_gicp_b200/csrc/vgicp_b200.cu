@@ -27,8 +27,10 @@ template <typename T>
 struct DevBuf {  // grow-only device array
   T* p = nullptr;
   size_t cap = 0;
+  bool external = false;  // points into memory owned elsewhere (the multi-GPU exchange arena): fixed capacity, never freed here
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
+    if (external) return cudaErrorMemoryAllocation;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -38,9 +40,16 @@ struct DevBuf {  // grow-only device array
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && !external) cudaFree(p);
     p = nullptr;
     cap = 0;
+    external = false;
+  }
+  void attach(T* q, size_t capacity) {  // switch to external storage
+    release();
+    p = q;
+    cap = capacity;
+    external = true;
   }
 };
 
@@ -59,6 +68,10 @@ struct Cloud {
   cudaEvent_t ready = nullptr;
   DevBuf<unsigned char> staging;
   DevBuf<unsigned char> knn_scratch;
+  const float4* knn_sorted = nullptr;  // the cloud in the k-NN grid's Morton order (inside knn_scratch), original index in .w
+  int knn_q_begin = 0, knn_q_end = 0;  // sorted positions whose neighbour rows the last find_neighbors computed
+  int arena_slot = 0;                  // which half of the exchange arena holds this cloud's covariances (stage-1 sharding)
+  unsigned long long arena_seq = 0;    // slices delivered for this cloud so far
   void release() { pts.release(); nbr.release(); covA.release(); covB.release(); staging.release(); knn_scratch.release(); }
 };
 
@@ -131,6 +144,11 @@ struct vgicp_context {
   int comm_rank = 0, comm_ranks = 0;
   unsigned long long comm_seq = 0;
   int shard_begin = 0, shard_end = -1;           // evaluations cover source points [begin, end)
+  // stage-1 sharding: exchange arena (covariances of both clouds + delivery flags), own and peers' (IPC-mapped)
+  unsigned char* arena = nullptr;
+  unsigned char* arena_peers[kCommMaxRanks] = {};
+  size_t arena_points = 0;
+  int stage1_sharding = 0;
   int speculate = 1;  // LM trial evaluations also linearise at the trial pose (vgicp_set_speculation)
   int exec_hint = 0;  // 0 = latency (one registration should finish as soon as possible), 1 = throughput (many concurrent handles)
   int align_mode = 1;  // 1 = host-driven loop over the evaluation kernels (default: faster today), 0 = device-resident LM chain
@@ -294,13 +312,23 @@ int find_neighbors(vgicp_handle h, Cloud& c, int k) {
   CU_TRY(h, c.nbr.reserve((size_t)c.n * k));
   cudaError_t ke = cudaSuccess;
   if (h->knn_mode == 2) {  // legacy one-thread-per-query scan, kept for A/B measurements
+    c.knn_sorted = nullptr;
+    c.knn_q_begin = 0;
+    c.knn_q_end = c.n;
     KLAUNCH_ST(h, c.st, VGICP_PROF_KNN, ke = launch_knn_bruteforce(c.pts.p, c.n, k, c.nbr.p, c.st));
   } else {
     const size_t need = knn_grid_scratch_bytes(c.n, nullptr, nullptr);
     CU_TRY(h, c.knn_scratch.reserve(need));
     int nl = 0;
-    KLAUNCH_ST(h, c.st, VGICP_PROF_KNN,
-            ke = launch_knn_grid(c.pts.p, c.n, k, c.nbr.p, c.knn_scratch.p, c.knn_scratch.cap, (h->knn_mode == 1 || c.n < 256) ? 1 : 0, 0, c.n, &nl, c.st));
+    c.knn_q_begin = 0;
+    c.knn_q_end = c.n;
+    if (h->stage1_sharding && h->comm_ranks > 1 && h->arena_peers[h->comm_rank]) {  // this rank's slice of the queries (sorted positions)
+      const long long base = c.n / h->comm_ranks, rem = c.n % h->comm_ranks, r = h->comm_rank;
+      c.knn_q_begin = (int)(r * base + (r < rem ? r : rem));
+      c.knn_q_end = c.knn_q_begin + (int)base + (r < rem ? 1 : 0);
+    }
+    KLAUNCH_ST(h, c.st, VGICP_PROF_KNN, ke = launch_knn_grid(c.pts.p, c.n, k, c.nbr.p, c.knn_scratch.p, c.knn_scratch.cap, (h->knn_mode == 1 || c.n < 256) ? 1 : 0, c.knn_q_begin,
+                                                            c.knn_q_end, &nl, &c.knn_sorted, c.st));
     h->launches += nl > 0 ? nl - 1 : 0;
   }
   CU_TRY(h, ke);
@@ -314,7 +342,27 @@ int calc_covariances(vgicp_handle h, Cloud& c, int method) {
   if (method < 0 || method > 4) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "calculate_covariances: bad regularization method");
   CU_TRY(h, c.covA.reserve(c.n));
   CU_TRY(h, c.covB.reserve(c.n));
-  if (c.n > 0) {
+  const bool sharded = h->stage1_sharding && h->comm_ranks > 1 && h->arena_peers[h->comm_rank] && c.knn_sorted && (c.knn_q_begin > 0 || c.knn_q_end < c.n);
+  if (c.n > 0 && sharded) {
+    // this rank computed the neighbour rows of a slice only: covariances of that slice go straight into every rank's arena
+    // (peer stores), then the ranks tell each other and wait -- all in stream order, the host does not block
+    if ((size_t)c.n > h->arena_points) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "calculate_covariances: cloud larger than the exchange arena (vgicp_comm_export_arena max_points)");
+    float4* pa[kCommMaxRanks];
+    float2* pb[kCommMaxRanks];
+    ArenaPeers ap;
+    for (int r = 0; r < kCommMaxRanks; r++) {
+      unsigned char* base = r < h->comm_ranks ? h->arena_peers[r] : nullptr;
+      ap.hdr[r] = reinterpret_cast<CommArenaHeader*>(base);
+      pa[r] = base ? reinterpret_cast<float4*>(base + kCommArenaHeaderBytes + (size_t)c.arena_slot * h->arena_points * 24) : nullptr;
+      pb[r] = base ? reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(pa[r]) + h->arena_points * 16) : nullptr;
+    }
+    cudaError_t ke = cudaSuccess;
+    KLAUNCH_ST(h, c.st, VGICP_PROF_COVARIANCE, ke = launch_covariance_knn_sharded(c.pts.p, c.nbr.p, c.knn_sorted, c.knn_q_begin, c.knn_q_end, c.k, method, pa, pb, h->comm_ranks, c.st));
+    CU_TRY(h, ke);
+    c.arena_seq++;
+    KLAUNCH_ST(h, c.st, VGICP_PROF_COVARIANCE, k_comm_deliver_and_wait<<<1, 32, 0, c.st>>>(ap, h->comm_rank, h->comm_ranks, c.arena_slot, c.arena_seq));
+    CU_TRY(h, cudaGetLastError());
+  } else if (c.n > 0) {
     cudaError_t ke = cudaSuccess;
     KLAUNCH_ST(h, c.st, VGICP_PROF_COVARIANCE, ke = launch_covariance_knn(c.pts.p, c.nbr.p, c.n, c.k, method, c.covA.p, c.covB.p, c.st));
     CU_TRY(h, ke);
@@ -845,6 +893,7 @@ int vgicp_destroy(vgicp_handle h) {
   h->staging.release();
   if (h->comm_ranks > 1) vgicp_comm_shutdown(h);
   if (h->comm_box) cudaFree(h->comm_box);
+  if (h->arena) cudaFree(h->arena);
   h->partials.release();
   h->corr_ids.release();
   if (h->d_ticket) cudaFree(h->d_ticket);
@@ -1435,10 +1484,69 @@ int vgicp_comm_init(vgicp_handle h, int rank, int nranks, const unsigned char* a
   return VGICP_OK;
 }
 
+// ---- stage-1 sharding: the exchange arena ----
+int vgicp_comm_export_arena(vgicp_handle h, size_t max_points, unsigned char* handle64) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (!handle64 || max_points == 0 || max_points > ((size_t)1 << 28)) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "comm_export_arena: bad argument");
+  if (h->arena && h->arena_points != max_points) return fail(h, VGICP_ERR_BAD_STATE, "comm_export_arena: arena already allocated with another capacity");
+  if (!h->arena) {
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream_b));
+    const size_t bytes = kCommArenaHeaderBytes + 2 * max_points * 24;
+    CU_TRY(h, cudaMalloc(&h->arena, bytes));
+    CU_TRY(h, cudaMemset(h->arena, 0, bytes));
+    h->arena_points = max_points;
+    // the covariance arrays of both clouds now live in the arena (previous covariances are dropped)
+    Cloud* cl[2] = {&h->target, &h->source};
+    for (int j = 0; j < 2; j++) {
+      unsigned char* base = h->arena + kCommArenaHeaderBytes + (size_t)j * max_points * 24;
+      cl[j]->covA.attach(reinterpret_cast<float4*>(base), max_points);
+      cl[j]->covB.attach(reinterpret_cast<float2*>(base + max_points * 16), max_points);
+      cl[j]->arena_slot = j;
+      cl[j]->arena_seq = 0;
+      cl[j]->has_cov = false;
+    }
+    h->map.built = false;
+    h->map.pending = false;
+  }
+  cudaIpcMemHandle_t ipc;
+  CU_TRY(h, cudaIpcGetMemHandle(&ipc, h->arena));
+  memcpy(handle64, &ipc, 64);
+  return VGICP_OK;
+}
+
+int vgicp_comm_init_arena(vgicp_handle h, const unsigned char* all_handles) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  if (!all_handles) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "comm_init_arena: null handles");
+  if (h->comm_ranks < 1 || !h->arena) return fail(h, VGICP_ERR_BAD_STATE, "comm_init_arena: call vgicp_comm_init and vgicp_comm_export_arena first");
+  for (int r = 0; r < h->comm_ranks; r++) {
+    if (r == h->comm_rank) { h->arena_peers[r] = h->arena; continue; }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, all_handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(h, VGICP_ERR_COMM, std::string("comm_init_arena: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    h->arena_peers[r] = reinterpret_cast<unsigned char*>(p);
+  }
+  return VGICP_OK;
+}
+
+int vgicp_set_stage1_sharding(vgicp_handle h, int enable) {
+  CHECK_HANDLE(h);
+  h->stage1_sharding = enable ? 1 : 0;
+  return VGICP_OK;
+}
+
 int vgicp_comm_shutdown(vgicp_handle h) {
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream_b) cudaStreamSynchronize(h->stream_b);
+  for (int r = 0; r < h->comm_ranks; r++)
+    if (r != h->comm_rank && h->arena_peers[r]) cudaIpcCloseMemHandle(h->arena_peers[r]);
+  for (int r = 0; r < kCommMaxRanks; r++) h->arena_peers[r] = nullptr;
   for (int r = 0; r < h->comm_ranks; r++)
     if (r != h->comm_rank && h->comm_peers[r]) cudaIpcCloseMemHandle(h->comm_peers[r]);
   for (int r = 0; r < kCommMaxRanks; r++) h->comm_peers[r] = nullptr;
@@ -1456,6 +1564,11 @@ int vgicp_comm_error(vgicp_handle h, int* error) {
     CommMailbox tmp;
     CU_TRY(h, cudaMemcpy(&tmp, h->comm_box, sizeof(CommMailbox), cudaMemcpyDeviceToHost));
     *error = tmp.error;
+  }
+  if (h->arena) {
+    CommArenaHeader hdr;
+    CU_TRY(h, cudaMemcpy(&hdr, h->arena, sizeof(hdr), cudaMemcpyDeviceToHost));
+    *error |= hdr.error;
   }
   return VGICP_OK;
 }

@@ -38,6 +38,13 @@ struct Pose {      // float image of an Eigen::Isometry3f: R row-major here, t
 };
 
 constexpr int kCommMaxRanks = 8;
+// Stage-1 sharding: per rank one IPC-exported arena holding the covariance arrays of both clouds (so that peers can store the
+// covariances of their slice straight into it) and the "slice delivered" flags.
+struct CommArenaHeader {
+  volatile unsigned long long delivered[2][kCommMaxRanks];  // [cloud slot][sender rank] = sequence number of the last delivered slice
+  volatile int error;
+};
+constexpr size_t kCommArenaHeaderBytes = 256;
 // one per rank, in that rank's device memory, mapped into every peer with CUDA IPC
 struct CommMailbox {
   double vals[2][kCommMaxRanks][32];                 // [seq & 1][sender][28 sums]
@@ -137,6 +144,25 @@ __device__ __forceinline__ int dense_offset(const DenseIndex& d, int x, int y, i
 __global__ void k_fill_i32(int* __restrict__ p, int v, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+}
+
+// after a sharded covariance kernel (stream order): make this rank's peer stores visible, tell every rank that the slice of cloud
+// slot `slot` number `seq` has been delivered, and wait until every rank's slice of it has arrived here
+struct ArenaPeers {
+  CommArenaHeader* hdr[kCommMaxRanks];
+};
+__global__ void k_comm_deliver_and_wait(ArenaPeers peers, int rank, int nranks, int slot, unsigned long long seq) {
+  __threadfence_system();
+  if ((int)threadIdx.x < nranks) {
+    peers.hdr[threadIdx.x]->delivered[slot][rank] = seq;
+    __threadfence_system();
+    CommArenaHeader* me = peers.hdr[rank];
+    long long spins = 0;
+    while (me->delivered[slot][threadIdx.x] < seq) {
+      if (++spins > (1LL << 31)) { me->error = 1; break; }
+    }
+  }
+  __threadfence_system();
 }
 
 // set_{source,target}_neighbors: flag any caller-supplied neighbour index outside [0, n)

@@ -255,6 +255,47 @@ __global__ void __launch_bounds__(128) k_covariance_knn(const float4* __restrict
   store_cov_sym(c, covA, covB, i);
 }
 
+// The same for a slice of the cloud when stage 1 is sharded over several GPUs: thread t takes the point at sorted
+// position pos_begin + t of the k-NN grid (the slice whose neighbour rows this rank computed) and stores its covariance into the
+// covariance arrays of EVERY rank -- plain peer stores over NVLink into IPC-mapped memory, own copy included -- so that each rank
+// ends up with the covariances of the whole cloud without a collective call.
+struct CovPeers {
+  float4* covA[8];
+  float2* covB[8];
+  int nranks;
+};
+__global__ void __launch_bounds__(128) k_covariance_knn_sharded(const float4* __restrict__ pts, const int* __restrict__ nbr, const float4* __restrict__ sorted, int pos_begin, int pos_end,
+                                                               int k, int method, CovPeers peers) {
+  const int pos = pos_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= pos_end) return;
+  const int i = __float_as_int(sorted[pos].w);
+  float mx = 0.f, my = 0.f, mz = 0.f;
+  float cxx = 0.f, cxy = 0.f, cxz = 0.f, cyy = 0.f, cyz = 0.f, czz = 0.f;
+  const int* row = nbr + (size_t)i * k;
+  for (int j = 0; j < k; j++) {
+    float4 p = pts[row[j]];
+    mx = __fadd_rn(mx, p.x); my = __fadd_rn(my, p.y); mz = __fadd_rn(mz, p.z);
+    cxx = __fmaf_rn(p.x, p.x, cxx); cxy = __fmaf_rn(p.x, p.y, cxy); cxz = __fmaf_rn(p.x, p.z, cxz);
+    cyy = __fmaf_rn(p.y, p.y, cyy); cyz = __fmaf_rn(p.y, p.z, cyz); czz = __fmaf_rn(p.z, p.z, czz);
+  }
+  float kf = (float)k;
+  mx = __fdiv_rn(mx, kf); my = __fdiv_rn(my, kf); mz = __fdiv_rn(mz, kf);
+  float c[9];
+  c[0] = __fmaf_rn(-mx, mx, __fdiv_rn(cxx, kf));
+  c[1] = c[3] = __fmaf_rn(-mx, my, __fdiv_rn(cxy, kf));
+  c[2] = c[6] = __fmaf_rn(-mx, mz, __fdiv_rn(cxz, kf));
+  c[4] = __fmaf_rn(-my, my, __fdiv_rn(cyy, kf));
+  c[5] = c[7] = __fmaf_rn(-my, mz, __fdiv_rn(cyz, kf));
+  c[8] = __fmaf_rn(-mz, mz, __fdiv_rn(czz, kf));
+  regularize_cov(c, method);
+  const float4 a4 = make_float4(c[0], 0.5f * (c[1] + c[3]), 0.5f * (c[2] + c[6]), c[4]);
+  const float2 b2 = make_float2(0.5f * (c[5] + c[7]), c[8]);
+  for (int r = 0; r < peers.nranks; r++) {
+    peers.covA[r][i] = a4;
+    peers.covB[r][i] = b2;
+  }
+}
+
 // exp(x) for x <= 0 from IEEE single operations only (Cephes' expf: n = rint(x log2 e), two-step reduction r = x - n ln 2,
 // degree-5 polynomial, scale by 2^n), every operation spelled, so that the CPU checker evaluates the identical sequence.
 // Why not expf: the reference calls CUDA's expf, a 2-ulp function that no CPU libm reproduces bit for bit; this one has the same
@@ -588,73 +629,36 @@ __device__ __forceinline__ float knn_d2(float4 q, float4 t) {  // (dx*dx + dy*dy
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-constexpr int kSearchThreads = 128;
-constexpr int kDeferCandidates = 768;  // blocks with more candidates than this go to the block-cooperative kernel (~1 % of the queries of a
-                                       // LiDAR scan: density transitions, where a lone thread would stall its warp for thousands of points)
-// nearest-first order of the 3x3x3 block (index = 9*(dx+1) + 3*(dy+1) + (dz+1)): centre, 6 faces, 12 edges, 8 corners
-__constant__ unsigned char kBlockOrder[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25, 0, 2, 6, 8, 18, 20, 24, 26};
+// compare-exchange step of a bitonic network over the 32 lanes: lane keeps the smaller key when keep_min
+__device__ __forceinline__ void cmpx(tkey& e, int stride, bool keep_min) {
+  tkey o = __shfl_xor_sync(0xffffffffu, e, stride);
+  if ((o < e) == keep_min) e = o;  // keys are distinct except (inf, INT_MAX) padding, where either choice is the same
+}
 
-// Per-thread candidate buffer in shared memory, [slot][thread] (bank = thread: conflict-free whatever slot each lane touches).
-// Everything a thread does with it is a plain counted loop -- count the keys below a threshold, compact, rank -- so the lanes of a
-// warp stay converged and the loops have instruction-level parallelism (a heap or a sorted insertion would be a dependent chain of
-// shared-memory accesses behind a branch that some lane of the warp takes at almost every candidate).
-#define KNN_BUF(j) buf[(j) * kSearchThreads + threadIdx.x]
-#define KNN_BUF_HI(j) reinterpret_cast<const unsigned*>(buf)[((j) * kSearchThreads + threadIdx.x) * 2 + 1]
+constexpr int kSearchWarps = 8;          // queries per block of the search kernel
+constexpr int kWarpBuf = 128;            // per-warp buffer of candidate keys within the bound
+constexpr int kDeferCandidates = 2048;   // blocks with more candidates than this go to the block-cooperative kernel (density transitions)
 
-// Smallest-ish threshold T on the distance bits (the high word of the keys) such that at least k of the cnt buffered keys have
-// distance bits <= T: bisection on the bit pattern (non-negative floats order like their bits), stopping early once at most
-// k + slack keys qualify.  `hi` must qualify on entry (count(<= hi) >= k).
-__device__ __noinline__ unsigned tighten_threshold(const tkey* buf, int cnt, int k, int slack, unsigned hi) {
+// Smallest-ish threshold T on distance bits with at least k of the warp's values <= T (each lane holds NV values; absent = 0xFFFFFFFF):
+// bisection on the bit pattern (non-negative floats order like their bits), one ballot per value and step, stopping as soon as at
+// most `limit` values qualify.  `hi` must qualify on entry.  All lanes return the same T.
+template <int NV>
+__device__ __forceinline__ unsigned warp_tighten(const unsigned (&v)[NV], int k, int limit, unsigned hi) {
   unsigned lo = 0;
   while (hi - lo > 1u) {
     const unsigned mid = lo + ((hi - lo) >> 1);
     int c = 0;
-    for (int j = 0; j < cnt; j++) c += KNN_BUF_HI(j) <= mid ? 1 : 0;
+#pragma unroll
+    for (int j = 0; j < NV; j++) c += __popc(__ballot_sync(0xffffffffu, v[j] <= mid));
     if (c >= k) {
       hi = mid;
-      if (c <= k + slack) break;
+      if (c <= limit) break;
     } else {
       lo = mid;
     }
   }
   return hi;
 }
-// keep the keys whose distance bits are <= T (stable, in place); returns the new count
-__device__ __noinline__ int compact_below(tkey* buf, int cnt, unsigned T) {
-  int w = 0;
-  for (int j = 0; j < cnt; j++) {
-    const tkey e = KNN_BUF(j);
-    if ((unsigned)(e >> 32) <= T) KNN_BUF(w++) = e;
-  }
-  return w;
-}
-
-// candidates sorted[st .. en): those within the bound T are appended to the buffer (four loads in flight); a full buffer is tightened
-// to (about) the k-th distance of what it holds.  Returns the new count, or -1 when the buffer cannot be tightened (ties).
-// Not inlined: the caller's nine-cell rounds are unrolled, and nine copies of this body would not fit the instruction cache.
-__device__ __noinline__ int scan_cell(tkey* buf, int cnt, unsigned& T, float4 q, const float4* __restrict__ sorted, int st, int en, int k, int cap) {
-  for (int p0 = st; p0 < en; p0 += 4) {
-    float4 c[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) c[u] = __ldg(&sorted[min(p0 + u, en - 1)]);
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const float d2 = knn_d2(q, c[u]);
-      if (p0 + u < en && __float_as_uint(d2) <= T) {
-        KNN_BUF(cnt) = make_key(d2, __float_as_int(c[u].w));
-        cnt++;
-      }
-    }
-    if (cnt > cap - 4) {
-      T = tighten_threshold(buf, cnt, k, (k >> 3) + 1, T);
-      cnt = compact_below(buf, cnt, T);
-      if (cnt > cap - 8) return -1;
-    }
-  }
-  return cnt;
-}
-
-__device__ __forceinline__ unsigned long long sel3(const unsigned long long* v, int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : v[2]); }  // (selects, not a dynamic index)
 
 // finest level l >= l_min with 0.998 s_l >= B (L when there is none); s = that level's cell size
 __device__ __forceinline__ int level_for(float B, int l_min, int L, float s0, float& s) {
@@ -664,124 +668,199 @@ __device__ __forceinline__ int level_for(float B, int l_min, int L, float s0, fl
   return l;
 }
 
-__global__ void __launch_bounds__(kSearchThreads, 3) k_knn_search(GridArgs a, int cap, int force_whole_cloud) {
-  extern __shared__ tkey buf[];  // [cap][kSearchThreads]
-  const int i = a.q_begin + blockIdx.x * kSearchThreads + threadIdx.x;
+// One warp per query (sorted position i); every step is warp-synchronous, so the lanes never diverge:
+//   1. the 64 points around position i in Morton order (two coalesced loads): the k-th smallest of their distances, found by a
+//      warp bisection (ballot + popc per step), bounds the k-th distance from above;
+//   2. the finest level l with 0.998 s_l >= bound: every point within the bound of the query lies in the 3x3x3 block of its cell
+//      there (window points included); 27 lanes look the block's cells up in parallel, cells whose box is beyond the bound are dropped;
+//   3. the cells' runs are flattened into one index space (prefix sum over the lanes) and read 32 candidates at a time; those within
+//      the bound are appended (ballot + prefix) to the warp's buffer in shared memory -- nothing is sorted while scanning;
+//   4. the buffer is tightened to at most 32 (64 for k > 32) keys by another bisection, the survivors are sorted once across the
+//      lanes (bitonic network on 64-bit keys) and the first k are the row, ascending in (d2, index).
+template <bool WIDE>
+__global__ void __launch_bounds__(kSearchWarps * 32) k_knn_search(GridArgs a, int force_whole_cloud) {
+  __shared__ tkey sbuf[kSearchWarps][kWarpBuf];
+  __shared__ tkey sfin[kSearchWarps][64];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int i = a.q_begin + blockIdx.x * kSearchWarps + wid;
   if (i >= a.q_end) return;
   const int k = a.k, L = a.L;
   const GridGeom g = grid_geom(a.bbox_min, a.bbox_max, L);
   const float4 q = __ldg(&a.sorted[i]);
   const int qi = __float_as_int(q.w);
   if (force_whole_cloud) {
-    a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, L);
+    if (lane == 0) a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, L);
     return;
   }
-  // 1. Morton window: the k-th smallest of the distances to the ~3k points around position i bounds the k-th distance from above
-  unsigned T;  // threshold on the distance bits; invariant: at least k points of the cloud have distance bits <= T
+  tkey* buf = sbuf[wid];
+  // 1. Morton window -> bound on the k-th distance (k <= 64 <= window size whenever n >= 64; a smaller cloud is all window)
+  unsigned T;
   {
-    const int h = min(k + (k >> 1) < 8 ? 8 : k + (k >> 1), (cap - 1) / 2);
-    int wlo = i - h, whi = i + h;
-    if (wlo < 0) { whi -= wlo; wlo = 0; }
-    if (whi > a.n - 1) { wlo -= whi - (a.n - 1); whi = a.n - 1; }
-    if (wlo < 0) wlo = 0;
-    const int cnt = whi - wlo + 1;  // >= k (n >= k, h >= k)
-    unsigned mx = 0;
-    for (int j = 0; j < cnt; j++) {
-      const float4 c = __ldg(&a.sorted[wlo + j]);
-      const tkey key = make_key(knn_d2(q, c), __float_as_int(c.w));
-      KNN_BUF(j) = key;
-      mx = max(mx, (unsigned)(key >> 32));
+    int w0 = i - 32;
+    if (w0 > a.n - 64) w0 = a.n - 64;
+    if (w0 < 0) w0 = 0;
+    unsigned v[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int p = w0 + u * 32 + lane;
+      v[u] = 0xFFFFFFFFu;
+      if (p < a.n) v[u] = __float_as_uint(knn_d2(q, __ldg(&a.sorted[p])));
     }
-    T = tighten_threshold(buf, cnt, k, (k >> 3) + 1, mx);
+    T = warp_tighten<2>(v, k, k + (k >> 2) + 1, 0x7f800000u);
   }
   const int l_min = *a.l_min;
   float s;
   const int l = level_for(sqrtf(__uint_as_float(T)), l_min, L, g.s0, s);
   if (l >= L) {  // the bound exceeds the coarsest cells (tiny cloud, far outlier): whole cloud, block-cooperative
-    a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, L);
+    if (lane == 0) a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, L);
     return;
   }
-  // 2. the 3x3x3 block of that level holds every point within the bound of the query (window points included): the cells whose box
-  //    lies within the bound are scanned, candidates within the bound are appended to the buffer
-  const int3 c0 = grid_cell0(g, q.x, q.y, q.z);
-  const int cqx = c0.x >> l, cqy = c0.y >> l, cqz = c0.z >> l, cl_max = g.cmax >> l;
-  const float fx = q.x - g.minx, fy = q.y - g.miny, fz = q.z - g.minz;
-  const float slack = 2e-3f * s;  // rounding of the cell boundaries
-  // Morton bits of the three cell coordinates per axis (a neighbour's code is an OR of three of them)
-  unsigned long long mx[3], my[3], mz[3];
-#pragma unroll
-  for (int d = 0; d < 3; d++) {
-    mx[d] = spread3((unsigned)(cqx + d - 1)) << 2;
-    my[d] = spread3((unsigned)(cqy + d - 1)) << 1;
-    mz[d] = spread3((unsigned)(cqz + d - 1));
-  }
-  int cnt = 0, scanned = 0;
-#pragma unroll 1
-  for (int b = 0; b < 3; b++) {  // nine cells per round: their table probes are in flight together
-    uint4 e[9];
-    unsigned long long ckey[9];
-    float box2[9];
-    bool want[9];
-    {
-      const float reach = sqrtf(__uint_as_float(T)) + slack;
-      const float reach2 = reach * reach;
-#pragma unroll
-      for (int j = 0; j < 9; j++) {
-        const int oo = kBlockOrder[b * 9 + j];
-        const int cx = cqx + oo / 9 - 1, cy = cqy + (oo / 3) % 3 - 1, cz = cqz + oo % 3 - 1;
-        // distance from the query to the cell's box against the bound (+ slack)
-        const float lx = cx * s, ly = cy * s, lz = cz * s;
-        const float ex = fmaxf(fmaxf(lx - fx, fx - (lx + s)), 0.f), ey = fmaxf(fmaxf(ly - fy, fy - (ly + s)), 0.f), ez = fmaxf(fmaxf(lz - fz, fz - (lz + s)), 0.f);
-        box2[j] = ex * ex + ey * ey + ez * ez;
-        want[j] = (unsigned)cx <= (unsigned)cl_max && (unsigned)cy <= (unsigned)cl_max && (unsigned)cz <= (unsigned)cl_max && box2[j] <= reach2;
-        ckey[j] = ((sel3(mx, oo / 9) | sel3(my, (oo / 3) % 3) | sel3(mz, oo % 3)) << 4) | (unsigned)l;
-        if (want[j]) e[j] = __ldg(reinterpret_cast<const uint4*>(&a.table[grid_hash(ckey[j]) & a.tmask]));
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 9; j++) {
-      if (!want[j]) continue;
-      unsigned pos = grid_hash(ckey[j]) & a.tmask;
-      uint4 ent = e[j];
-      bool found = false;
-      for (;;) {
-        const unsigned long long cur = ((unsigned long long)ent.y << 32) | ent.x;
-        if (cur == ckey[j]) { found = true; break; }
-        if (cur == kGridEmpty) break;
-        pos = (pos + 1) & a.tmask;
-        ent = __ldg(reinterpret_cast<const uint4*>(&a.table[pos]));
-      }
-      if (!found) continue;
-      {
-        const float reach = sqrtf(__uint_as_float(T)) + slack;  // the bound may have tightened since the probe was issued
-        if (box2[j] > reach * reach) continue;
-      }
-      const int st = (int)ent.z, en = (int)ent.w;
-      scanned += en - st;
-      if (scanned > kDeferCandidates) {  // a lone thread would stall its warp: block-cooperative kernel (scans the block afresh)
-        a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, l);
-        return;
-      }
-      cnt = scan_cell(buf, cnt, T, q, a.sorted, st, en, k, cap);
-      if (cnt < 0) {  // ties (duplicate points) that a distance threshold cannot separate: cooperative kernel
-        a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, l);
-        return;
+  // 2. the block's cells, one per lane
+  int st = 0, cn = 0;
+  if (lane < 27) {
+    const int3 c0 = grid_cell0(g, q.x, q.y, q.z);
+    const int cl_max = g.cmax >> l;
+    const int cx = (c0.x >> l) + lane / 9 - 1, cy = (c0.y >> l) + (lane / 3) % 3 - 1, cz = (c0.z >> l) + lane % 3 - 1;
+    if ((unsigned)cx <= (unsigned)cl_max && (unsigned)cy <= (unsigned)cl_max && (unsigned)cz <= (unsigned)cl_max) {
+      // distance from the query to the cell's box against the bound (+ slack for the rounding of the cell boundaries)
+      const float fx = q.x - g.minx, fy = q.y - g.miny, fz = q.z - g.minz;
+      const float lx = cx * s, ly = cy * s, lz = cz * s;
+      const float ex = fmaxf(fmaxf(lx - fx, fx - (lx + s)), 0.f), ey = fmaxf(fmaxf(ly - fy, fy - (ly + s)), 0.f), ez = fmaxf(fmaxf(lz - fz, fz - (lz + s)), 0.f);
+      const float reach = sqrtf(__uint_as_float(T)) + 2e-3f * s;
+      if (ex * ex + ey * ey + ez * ez <= reach * reach) {
+        int en;
+        if (cell_range(a, (morton3(cx, cy, cz) << 4) | (unsigned)l, st, en)) cn = en - st;
       }
     }
   }
-  // 3. the k smallest of the buffered keys, ascending: tighten once more, then rank the survivors among themselves
-  T = tighten_threshold(buf, cnt, k, 2, T);
-  cnt = compact_below(buf, cnt, T);
-  int* row = a.nbr + (size_t)qi * k;
-  for (int j = 0; j < cnt; j++) {
-    const tkey ej = KNN_BUF(j);
-    int r = 0;
-    for (int m = 0; m < cnt; m++) r += KNN_BUF(m) < ej ? 1 : 0;
-    if (r < k) row[r] = key_index(ej);
+  // 3. flatten the runs and scan
+  int incl = cn;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  const int excl = incl - cn;
+  if (total > kDeferCandidates) {  // block-cooperative kernel (scans the block afresh)
+    if (lane == 0) a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, l);
+    return;
+  }
+  int cnt = 0;  // keys in the buffer (warp-uniform)
+  constexpr int U = 2;
+  for (int base = 0; base < total; base += 32 * U) {
+    float4 c[U];
+    bool valid[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int j = base + u * 32 + lane;
+      valid[u] = j < total;
+      c[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (base + u * 32 < total) {  // warp-uniform
+        int cell = 0;  // largest lane index whose exclusive prefix is <= j (runs of equal prefixes end at the non-empty cell)
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const int e = __shfl_sync(0xffffffffu, excl, (cell + step) & 31);
+          if (e <= j) cell += step;
+        }
+        const int cs = __shfl_sync(0xffffffffu, st, cell);
+        const int ce = __shfl_sync(0xffffffffu, excl, cell);
+        if (valid[u]) c[u] = __ldg(&a.sorted[cs + (j - ce)]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (base + u * 32 >= total) break;
+      const float d2 = knn_d2(q, c[u]);
+      const bool pass = valid[u] && __float_as_uint(d2) <= T;
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (pass) buf[cnt + __popc(m & lt)] = make_key(d2, __float_as_int(c[u].w));
+      cnt += __popc(m);
+      if (cnt > kWarpBuf - 32) {  // the next batch might not fit: tighten the bound to about the k-th distance of the buffered keys
+        __syncwarp();
+        unsigned v[kWarpBuf / 32];
+#pragma unroll
+        for (int t = 0; t < kWarpBuf / 32; t++) v[t] = t * 32 + lane < cnt ? (unsigned)(buf[t * 32 + lane] >> 32) : 0xFFFFFFFFu;
+        T = warp_tighten<kWarpBuf / 32>(v, k, k + (k >> 2) + 1, T);
+        tkey keep[kWarpBuf / 32];
+#pragma unroll
+        for (int t = 0; t < kWarpBuf / 32; t++) keep[t] = t * 32 + lane < cnt ? buf[t * 32 + lane] : kKeyInf;
+        __syncwarp();
+        int w = 0;
+#pragma unroll
+        for (int t = 0; t < kWarpBuf / 32; t++) {
+          const bool kp = v[t] <= T;
+          const unsigned mm = __ballot_sync(0xffffffffu, kp);
+          if (kp) buf[w + __popc(mm & lt)] = keep[t];
+          w += __popc(mm);
+        }
+        cnt = w;
+        __syncwarp();
+        if (cnt > kWarpBuf - 32) {  // ties (duplicate points) that a distance threshold cannot separate: cooperative kernel
+          if (lane == 0) a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, l);
+          return;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // 4. at most 32 (64) survivors -> one sort
+  constexpr int NF = WIDE ? 2 : 1;
+  {
+    unsigned v[kWarpBuf / 32];
+    tkey keep[kWarpBuf / 32];
+#pragma unroll
+    for (int t = 0; t < kWarpBuf / 32; t++) {
+      keep[t] = t * 32 + lane < cnt ? buf[t * 32 + lane] : kKeyInf;
+      v[t] = t * 32 + lane < cnt ? (unsigned)(keep[t] >> 32) : 0xFFFFFFFFu;
+    }
+    if (cnt > 32 * NF) T = warp_tighten<kWarpBuf / 32>(v, k, 32 * NF, T);
+    tkey* fin = sfin[wid];
+    fin[lane] = kKeyInf;
+    fin[32 + lane] = kKeyInf;
+    __syncwarp();
+    int w = 0;
+#pragma unroll
+    for (int t = 0; t < kWarpBuf / 32; t++) {
+      const bool kp = v[t] <= T;
+      const unsigned mm = __ballot_sync(0xffffffffu, kp);
+      const int dst = w + __popc(mm & lt);
+      if (kp && dst < 64) fin[dst] = keep[t];
+      w += __popc(mm);
+    }
+    __syncwarp();
+    if (w > 32 * NF) {  // more equal distances than the sort holds: cooperative kernel
+      if (lane == 0) a.defer_queue[atomicAdd(a.defer_count, 1)] = make_int2(i, l);
+      return;
+    }
+    tkey e0 = fin[lane], e1 = WIDE ? fin[32 + lane] : kKeyInf;
+    // bitonic sort of the 32 (64) keys across the lanes
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const bool up = (lane & size) == 0 || size == 32;
+        const bool lower = (lane & stride) == 0;
+        cmpx(e0, stride, lower == up);
+        if (WIDE) cmpx(e1, stride, lower != up);  // the second register is sorted descending: (e0, e1) is then bitonic
+      }
+    }
+    if (WIDE) {  // size == 32 sorted e1 descending over the lanes; merge the bitonic 64
+      const tkey lo_ = e0 < e1 ? e0 : e1, hi_ = e0 < e1 ? e1 : e0;
+      e0 = lo_;
+      e1 = hi_;
+#pragma unroll
+      for (int stride = 16; stride > 0; stride >>= 1) {
+        cmpx(e0, stride, (lane & stride) == 0);
+        cmpx(e1, stride, (lane & stride) == 0);
+      }
+    }
+    int* row = a.nbr + (size_t)qi * k;
+    if (lane < k) row[lane] = key_index(e0);
+    if (WIDE && 32 + lane < k) row[32 + lane] = key_index(e1);
   }
 }
-#undef KNN_BUF
-#undef KNN_BUF_HI
 
 // ---- warp-level sorted top-k (k <= 64) for the block-cooperative kernel: rank r lives in lane r & 31, register r >> 5.
 // WIDE=false (k <= 32) keeps a single register set. ----
@@ -791,12 +870,6 @@ struct WarpTopK {
 };
 
 __device__ __forceinline__ void topk_reset(WarpTopK& t) { t.e0 = t.e1 = t.worst = kKeyInf; }
-
-// compare-exchange step of a bitonic network over the 32 lanes: lane keeps the smaller key when keep_min
-__device__ __forceinline__ void cmpx(tkey& e, int stride, bool keep_min) {
-  tkey o = __shfl_xor_sync(0xffffffffu, e, stride);
-  if ((o < e) == keep_min) e = o;  // keys are distinct except (inf, INT_MAX) padding, where either choice is the same
-}
 
 // Merge a batch of 32 candidates into the sorted list (k <= 32): bitonic-sort the batch (15 steps), take the element-wise
 // minimum with the reversed list (the 32 smallest of the 64, a bitonic sequence), bitonic-merge (5 steps).
@@ -988,7 +1061,7 @@ size_t knn_grid_scratch_bytes(int n, int* levels_out, unsigned* table_size_out) 
 //                  [uninitialised: Morton codes x2 | sort values x2 | sorted points | deferred-query queue]
 // q_begin/q_end: sorted positions whose neighbours are searched (whole cloud: 0, n); the build always covers the whole cloud.
 cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned char* scratch, size_t scratch_bytes, int force_bruteforce, int q_begin, int q_end, int* launches,
-                            cudaStream_t stream) {
+                            const float4** sorted_out, cudaStream_t stream) {
   int L;
   unsigned T;
   size_t need = knn_grid_scratch_bytes(n, &L, &T);
@@ -1023,6 +1096,7 @@ cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned 
   a.sorted = reinterpret_cast<float4*>(p); p += (size_t)n * 16;
   a.defer_queue = reinterpret_cast<int2*>(p); p += (size_t)n * 8;
   a.codes = codes0;
+  if (sorted_out) *sorted_out = a.sorted;
   cudaError_t e;
   if ((e = cudaMemsetAsync(ff_begin, 0xFF, ff_bytes, stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(z_begin, 0, z_bytes, stream)) != cudaSuccess) return e;
@@ -1038,11 +1112,9 @@ cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned 
   nl += 2;
   const int nq = q_end > q_begin ? q_end - q_begin : 0;
   if (nq > 0) {
-    // candidate buffer per thread: the ~3k-point window of step 1 must fit, and the points within the bound of step 2 should
-    const int cap = k <= 20 ? 64 : (k <= 32 ? 104 : 200);
-    const size_t smem = (size_t)cap * kSearchThreads * sizeof(tkey);
-    if ((e = cudaFuncSetAttribute(k_knn_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)200 * kSearchThreads * sizeof(tkey)))) != cudaSuccess) return e;
-    k_knn_search<<<(nq + kSearchThreads - 1) / kSearchThreads, kSearchThreads, smem, stream>>>(a, cap, force_bruteforce);
+    const int sblocks = (nq + kSearchWarps - 1) / kSearchWarps;
+    if (k <= 32) k_knn_search<false><<<sblocks, kSearchWarps * 32, 0, stream>>>(a, force_bruteforce);
+    else k_knn_search<true><<<sblocks, kSearchWarps * 32, 0, stream>>>(a, force_bruteforce);
     int hblocks = (nq + kKnnGridWarps - 1) / kKnnGridWarps;
     if (hblocks > 148 * 4) hblocks = 148 * 4;  // persistent: items pulled from a counter
     if (k <= 32) k_knn_deferred<false><<<hblocks, kKnnGridWarps * 32, 0, stream>>>(a);
@@ -1055,6 +1127,17 @@ cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned 
 
 cudaError_t launch_covariance_knn(const float4* pts, const int* nbr, int n, int k, int method, float4* covA, float2* covB, cudaStream_t stream) {
   k_covariance_knn<<<(n + 127) / 128, 128, 0, stream>>>(pts, nbr, n, k, method, covA, covB);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_covariance_knn_sharded(const float4* pts, const int* nbr, const float4* sorted, int pos_begin, int pos_end, int k, int method, float4* const* covA_peers,
+                                         float2* const* covB_peers, int nranks, cudaStream_t stream) {
+  if (nranks < 1 || nranks > 8) return cudaErrorInvalidValue;
+  CovPeers peers;
+  for (int r = 0; r < 8; r++) { peers.covA[r] = r < nranks ? covA_peers[r] : nullptr; peers.covB[r] = r < nranks ? covB_peers[r] : nullptr; }
+  peers.nranks = nranks;
+  const int cnt = pos_end - pos_begin;
+  if (cnt > 0) k_covariance_knn_sharded<<<(cnt + 127) / 128, 128, 0, stream>>>(pts, nbr, sorted, pos_begin, pos_end, k, method, peers);
   return cudaGetLastError();
 }
 

@@ -22,7 +22,11 @@ cudaError_t launch_knn_bruteforce(const float4* pts, int n, int k, int* nbr, cud
 // aligned.  [q_begin, q_end): the sorted positions whose rows are computed (0, n = all; a slice per rank when stage 1 is sharded)
 size_t knn_grid_scratch_bytes(int n, int* levels_out, unsigned* table_size_out);
 cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned char* scratch, size_t scratch_bytes, int force_bruteforce, int q_begin, int q_end, int* launches,
-                            cudaStream_t stream);
+                            const float4** sorted_out, cudaStream_t stream);
+// covariances of the points at sorted positions [pos_begin, pos_end) of that grid, stored into the covariance arrays of all `nranks`
+// ranks (peer-mapped pointers; the own arrays included)
+cudaError_t launch_covariance_knn_sharded(const float4* pts, const int* nbr, const float4* sorted, int pos_begin, int pos_end, int k, int method, float4* const* covA_peers,
+                                         float2* const* covB_peers, int nranks, cudaStream_t stream);
 // covariance_estimation + covariance_regularization(method) fused; symmetric-packed output
 cudaError_t launch_covariance_knn(const float4* pts, const int* nbr, int n, int k, int method, float4* covA, float2* covB, cudaStream_t stream);
 // covariance_estimation_rbf + covariance_regularization(method); boxes: scratch of 6 floats per 512-point block (2 launches)

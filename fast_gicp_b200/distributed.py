@@ -58,6 +58,32 @@ def aggregate_throughput(local_units, local_ms, device="cpu"):
     return total / (worst * 1e-3), worst
 
 
+def _all_gather_bytes(blob):
+    """All-gather of one equal-length byte string per rank (any backend: the tensor lives where the backend wants it)."""
+    world = dist.get_world_size()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.tensor(list(blob), dtype=torch.uint8, device=dev)
+    out = [torch.zeros(len(blob), dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return [bytes(t.cpu().tolist()) for t in out]
+
+
+def setup_source_sharding(core, n_source, max_points=0):
+    """Wire one handle per rank for a sharded registration: exchange the IPC handles of the result mailboxes (and of
+    the covariance arena when max_points > 0 -> stage 1 sharded too), set this rank's slice of the source, barrier.
+    Returns (begin, end) of the slice.  The process group must be initialised (one rank per GPU)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    core.comm_init(rank, world, _all_gather_bytes(core.comm_export()))
+    if max_points > 0:
+        core.comm_init_arena(_all_gather_bytes(core.comm_export_arena(max_points)))
+    lo, hi = partition(n_source, rank, world)
+    core.set_source_shard(lo, hi)
+    dist.barrier()  # every mailbox / arena is cleared and mapped before anyone launches into it
+    if max_points > 0:
+        core.set_stage1_sharding(True)
+    return lo, hi
+
+
 def finalize():
     if dist.is_initialized():
         dist.destroy_process_group()

@@ -171,6 +171,16 @@ VGICP_API int vgicp_comm_init(vgicp_handle h, int rank, int nranks, const unsign
 VGICP_API int vgicp_comm_shutdown(vgicp_handle h);
 VGICP_API int vgicp_comm_error(vgicp_handle h, int* error);  /* 1 when a wait for a peer timed out */
 VGICP_API int vgicp_set_source_shard(vgicp_handle h, size_t begin, size_t end);  /* evaluations cover source points [begin, end) */
+/* Stage 1 sharded as well (k-NN queries + covariances): every rank builds the k-NN grid of the whole cloud but searches
+ * only its 1/nranks slice of the queries, computes the covariances of that slice and stores them straight into the covariance arrays
+ * of EVERY rank (peer stores over NVLink from inside the covariance kernel); a one-block kernel then tells the peers and waits for
+ * their slices, in stream order.  For that the covariance arrays of both clouds live in an IPC-exported arena of fixed capacity:
+ * vgicp_comm_export_arena(max_points) after vgicp_comm_init, all-gather the 64-byte handles, vgicp_comm_init_arena, host barrier,
+ * vgicp_set_stage1_sharding(1).  All ranks must then make the same sequence of set_*_cloud / find_*_neighbors /
+ * calculate_*_covariances / swap calls.  get_*_neighbors returns this rank's rows only; the covariances are complete everywhere. */
+VGICP_API int vgicp_comm_export_arena(vgicp_handle h, size_t max_points, unsigned char* handle64);
+VGICP_API int vgicp_comm_init_arena(vgicp_handle h, const unsigned char* all_handles /* nranks x 64 bytes */);
+VGICP_API int vgicp_set_stage1_sharding(vgicp_handle h, int enable);
 VGICP_API int vgicp_clear_source_shard(vgicp_handle h);
 /* ---- NDT (next-tier component: fast_gicp::cuda::NDTCudaCore, include/fast_gicp/cuda/ndt_cuda.cuh:28-68, src/fast_gicp/cuda/ndt_cuda.cu) ----
  * The same handle solves the NDT problems: vgicp_set_problem selects VGICP (0, default), NDT point-to-distribution (1) or NDT

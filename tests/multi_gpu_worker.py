@@ -52,13 +52,7 @@ def main():
     full = c.align()
 
     # exchange IPC handles, shard the source
-    mine = torch.tensor(list(c.comm_export()), dtype=torch.uint8)
-    gathered = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
-    dist.all_gather(gathered, mine)
-    c.comm_init(rank, world, [bytes(g.tolist()) for g in gathered])
-    lo, hi = D.partition(len(src), rank, world)
-    c.set_source_shard(lo, hi)
-    dist.barrier()
+    lo, hi = D.setup_source_sharding(c, len(src))
 
     e_sh, H_sh, b_sh = c.linearize(T)
     err_only, _, _ = c.compute_error(T, want_H=False)
@@ -71,6 +65,28 @@ def main():
     ms_eval = 1e3 * (time.perf_counter() - t0) / reps
     dist.barrier()
     sharded = c.align()
+    # stage 1 sharded as well: a fresh handle whose k-NN queries and covariances are split over the ranks and exchanged by peer stores
+    c2 = Core(local)
+    c2.set_resolution(res)
+    c2.set_neighbor_search_method(method)
+    lo2, hi2 = D.setup_source_sharding(c2, len(src), max_points=max(len(src), len(tgt)))
+    torch.cuda.synchronize()
+    dist.barrier()
+    t1 = time.perf_counter()
+    c2.set_target_cloud(tgt)
+    c2.find_target_neighbors(20)
+    c2.calculate_target_covariances(REG_PLANE)
+    c2.create_target_voxelmap()
+    c2.set_source_cloud(src)
+    c2.find_source_neighbors(20)
+    c2.calculate_source_covariances(REG_PLANE)
+    full_sharded = c2.align()
+    ms_full_sharded = 1e3 * (time.perf_counter() - t1)
+    cov_equal = bool(np.array_equal(c2.get_source_covariances(), c.get_source_covariances()) and np.array_equal(c2.get_target_covariances(), c.get_target_covariances()))
+    err2 = c2.comm_error()
+    dist.barrier()
+    c2.comm_shutdown()
+    c2.close()
     out = {
         "rank": rank, "world": world, "shard": [lo, hi], "comm_error": c.comm_error(),
         "H_rel_diff_vs_full": float(np.abs(H_sh - H_full).max() / np.abs(H_full).max()),
@@ -79,6 +95,8 @@ def main():
         "H_sum": float(H_sh.sum()), "b": [float(x) for x in b_sh], "err": float(e_sh),
         "T": [float(x) for x in pose_from_c(sharded.T).reshape(-1)], "T_full": [float(x) for x in pose_from_c(full.T).reshape(-1)],
         "iters": [int(sharded.nr_iterations), int(full.nr_iterations)], "converged": bool(sharded.converged), "ms_per_evaluation": ms_eval,
+        "stage1_sharded_covariances_equal": cov_equal, "stage1_sharded_T": [float(x) for x in pose_from_c(full_sharded.T).reshape(-1)],
+        "stage1_sharded_iters": int(full_sharded.nr_iterations), "stage1_sharded_comm_error": err2, "ms_registration_stage1_sharded": ms_full_sharded,
     }
     print(json.dumps(out), flush=True)
     dist.barrier()

@@ -1,10 +1,11 @@
 """The Morton-grid k-NN's exactness argument, modelled on the CPU (no CUDA involved).
 
-fast_gicp_b200/csrc/vgicp_stage1.cu answers a query in three steps: (1) the 2k+1 points around it in Morton order of the finest
-grid cells give an upper bound B on the k-th distance; (2) the finest level l (cell size s_l = s_0 2^l, not below l_min) with
-0.998 s_l >= B is selected: every point within B of the query lies in the 3x3x3 block of the query's cell there; (3) the block's
-cells whose box is within the current k-th distance (+ 2e-3 s slack) are scanned.  Queries whose bound exceeds the coarsest cells
-scan the whole cloud.  This file restates those rules with the kernel's float32 cell arithmetic and checks, on adversarial
+fast_gicp_b200/csrc/vgicp_stage1.cu answers a query in three steps: (1) the 64 points around it in Morton order of the finest
+grid cells give an upper bound B on the k-th distance (the kernel stops its bisection at any threshold that at least k window
+points meet; the model uses the tightest one, the k-th smallest); (2) the finest level l (cell size s_l = s_0 2^l, not below
+l_min) with 0.998 s_l >= B is selected: every point within B of the query lies in the 3x3x3 block of the query's cell there;
+(3) the block's cells whose box is within B (+ 2e-3 s slack) are scanned and the k smallest (d2, index) keys kept.  Queries whose
+bound exceeds the coarsest cells scan the whole cloud.  This file restates those rules with the kernel's float32 cell arithmetic and checks, on adversarial
 clouds, that the rows equal the brute-force rows -- so a change of the rules (or of their rounding slack) that breaks exactness
 is caught here, before a GPU is involved.  The CUDA kernels themselves are checked against the oracle in tests/test_gpu_parity.py."""
 import numpy as np
@@ -82,9 +83,8 @@ class MortonGrid:
         """Row of the point at sorted position i, by the kernel's rules; stats collects the number of candidates looked at."""
         k, n = self.k, len(self.p)
         q = self.sorted[i]
-        h = max(k, 8)
-        wlo, whi = max(i - h, 0), min(i + h, n - 1)
-        pos = np.arange(wlo, whi + 1)
+        w0 = max(min(i - 32, n - 64), 0)
+        pos = np.arange(w0, min(w0 + 64, n))
         seen = len(pos)
 
         def best(pos):
@@ -95,6 +95,8 @@ class MortonGrid:
 
         pos, d2 = best(pos)
         B = f32(np.sqrt(d2[-1])) if len(pos) == k else f32(np.inf)
+        T = d2[-1] if len(pos) == k else f32(np.inf)  # threshold on the squared distance: fixed while the block is scanned
+        pos, d2 = pos[:0], d2[:0]  # the window only provides the bound; its points are found again in the block
         l, s = self.l_min, f32(np.ldexp(self.s0, self.l_min))
         while l < self.L and not (B <= f32(0.998) * s):
             l += 1
@@ -115,15 +117,15 @@ class MortonGrid:
                         continue
                     lo = c.astype(f32) * s
                     ex = np.maximum(np.maximum(lo - f, f - (lo + s)), f32(0.0)).astype(f32)
-                    reach = f32(np.sqrt(d2[-1])) + slack
+                    reach = B + slack
                     if f32((ex[0] * ex[0] + ex[1] * ex[1]) + ex[2] * ex[2]) > reach * reach:
                         continue
                     r = self.ranges[l].get(self.morton(c))
                     if r is None:
                         continue
                     cand = np.arange(r[0], r[1])
-                    cand = cand[(cand < wlo) | (cand > whi)]
                     seen += len(cand)
+                    cand = cand[d2_f32(q, self.sorted[cand]) <= T]
                     pos, d2 = best(np.concatenate([pos, cand]))
         if stats is not None:
             stats.append((seen, l))

@@ -47,6 +47,9 @@ def test_sharded_evaluation_matches_single_gpu():
         assert r["H_rel_diff_vs_full"] < 1e-6 and r["b_rel_diff_vs_full"] < 1e-5 and r["err_rel_diff_vs_full"] < 1e-6 and r["err_only_rel"] < 1e-6
         assert r["converged"] and r["iters"][0] == r["iters"][1]
         assert np.abs(np.array(r["T"]) - np.array(r["T_full"])).max() < 1e-6
+        # stage 1 sharded too: the exchanged covariances are the unsharded ones bit for bit, so the registration walks the same iterates
+        assert r["stage1_sharded_comm_error"] == 0 and r["stage1_sharded_covariances_equal"]
+        assert r["stage1_sharded_T"] == r["T"] and r["stage1_sharded_iters"] == r["iters"][0]
     # every rank holds bit-identical sums (same doubles added in rank order)
     for r in res[1:]:
         assert r["H_sum"] == res[0]["H_sum"] and r["b"] == res[0]["b"] and r["err"] == res[0]["err"] and r["T"] == res[0]["T"]
