@@ -64,23 +64,29 @@ __device__ __forceinline__ void sort_hist_add(unsigned* sh, int passes, bool val
   }
 }
 
-// One pass: stable scatter of (key, value) by digit `pass` of the key.  vin == nullptr: the values are the positions 0..n-1.
-// hist: the kSortBins global digit counts of this pass; state: [num_tiles][kSortBins], zero on entry; ticket: zero on entry.
-// GATHER: on the last pass the caller may pass a float4 array to be permuted along (out4[pos] = {in4[value].xyz, value as bits}).
+// shared memory of one scatter tile
+struct SortTileSmem {
+  unsigned warp_cnt[kSortWarps][kSortBins];  // per warp: digit counts, then (after the scan) offsets of the warp inside the tile
+  unsigned digit_base[kSortBins];            // output position of the tile's first key of each digit
+  unsigned scan_tmp[kSortWarps];
+  unsigned tile;
+};
+
+// One tile of one pass: stable scatter of (key, value) by digit `pass` of the key.  vin == nullptr: the values are the positions
+// 0..n-1.  hist: the kSortBins global digit counts of this pass; state: [num_tiles][kSortBins], zero before the pass.  Tiles may
+// be processed in any order in which a tile never starts before all lower-numbered tiles have started or finished (tickets, or a
+// persistent grid walking the tiles round-robin): a tile only ever waits for lower-numbered ones.
+// On the last pass the caller may pass a float4 array to be permuted along (out4[pos] = {in4[value].xyz, value as bits}).
+// Called by all kSortThreads threads of the block; ends with the tile's stores issued (no trailing barrier).
 template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads) k_sort_pass(const KeyT* __restrict__ kin, const unsigned* __restrict__ vin, KeyT* __restrict__ kout, unsigned* __restrict__ vout, int n,
-                                                            int pass, const unsigned* __restrict__ hist, unsigned* state, unsigned* ticket, const float4* __restrict__ in4,
-                                                            float4* __restrict__ out4) {
-  __shared__ unsigned warp_cnt[kSortWarps][kSortBins];  // per warp: digit counts, then (after the scan) offsets of the warp inside the tile
-  __shared__ unsigned digit_base[kSortBins];            // output position of the tile's first key of each digit
-  __shared__ unsigned scan_tmp[kSortWarps];
-  __shared__ unsigned s_tile;
+__device__ __forceinline__ void sort_pass_tile(SortTileSmem& sm, unsigned tile, const KeyT* __restrict__ kin, const unsigned* __restrict__ vin, KeyT* __restrict__ kout,
+                                               unsigned* __restrict__ vout, int n, int pass, const unsigned* __restrict__ hist, unsigned* state, const float4* __restrict__ in4,
+                                               float4* __restrict__ out4) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-  for (int i = tid; i < kSortWarps * kSortBins; i += kSortThreads) (&warp_cnt[0][0])[i] = 0;
+  __syncthreads();  // (the previous tile's shared memory is no longer read)
+  for (int i = tid; i < kSortWarps * kSortBins; i += kSortThreads) (&sm.warp_cnt[0][0])[i] = 0;
   __syncthreads();
-  const unsigned tile = s_tile;
   const int shift = pass * kSortRadixBits;
   const long long base = (long long)tile * kSortTile + (long long)w * (32 * kSortItems);
   KeyT key[kSortItems];
@@ -96,8 +102,8 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_pass(const KeyT* __restri
     const int leader = __ffs(peers) - 1;
     unsigned prev = 0;
     if (valid && lane == leader) {
-      prev = warp_cnt[w][d];
-      warp_cnt[w][d] = prev + (unsigned)__popc(peers);
+      prev = sm.warp_cnt[w][d];
+      sm.warp_cnt[w][d] = prev + (unsigned)__popc(peers);
     }
     prev = __shfl_sync(0xffffffffu, prev, leader);
     rank[r] = prev + (unsigned)__popc(peers & lt);  // keys of this warp's run with the same digit that come before this one
@@ -105,12 +111,13 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_pass(const KeyT* __restri
   }
   __syncthreads();
   // exclusive scan of the global digit counts (where each digit's output range starts)
-  unsigned gstart[kSortBins / kSortThreads];
+  constexpr int J = kSortBins / kSortThreads;
+  unsigned gstart[J];
   {
-    unsigned c[kSortBins / kSortThreads], sum = 0;
+    unsigned c[J], sum = 0;
 #pragma unroll
-    for (int j = 0; j < kSortBins / kSortThreads; j++) {  // thread t owns digits t*J .. t*J+J-1 (contiguous)
-      c[j] = hist[tid * (kSortBins / kSortThreads) + j];
+    for (int j = 0; j < J; j++) {  // thread t owns digits t*J .. t*J+J-1 (contiguous)
+      c[j] = *reinterpret_cast<const volatile unsigned*>(&hist[tid * J + j]);
       sum += c[j];
     }
     unsigned incl = sum;
@@ -119,20 +126,19 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_pass(const KeyT* __restri
       const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
-    if (lane == 31) scan_tmp[w] = incl;
+    if (lane == 31) sm.scan_tmp[w] = incl;
     __syncthreads();
     unsigned wbase = 0;
-    for (int ww = 0; ww < w; ww++) wbase += scan_tmp[ww];
+    for (int ww = 0; ww < w; ww++) wbase += sm.scan_tmp[ww];
     unsigned run = wbase + incl - sum;
 #pragma unroll
-    for (int j = 0; j < kSortBins / kSortThreads; j++) {
+    for (int j = 0; j < J; j++) {
       gstart[j] = run;
       run += c[j];
     }
   }
   // per digit: offsets of the warps inside the tile, the tile's count, and the counts of all preceding tiles (look-back)
   volatile unsigned* st = state;
-  constexpr int J = kSortBins / kSortThreads;
   unsigned run[J], excl[J];
 #pragma unroll
   for (int j = 0; j < J; j++) {
@@ -140,8 +146,8 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_pass(const KeyT* __restri
     run[j] = 0;
 #pragma unroll
     for (int ww = 0; ww < kSortWarps; ww++) {
-      const unsigned c = warp_cnt[ww][d];
-      warp_cnt[ww][d] = run[j];
+      const unsigned c = sm.warp_cnt[ww][d];
+      sm.warp_cnt[ww][d] = run[j];
       run[j] += c;
     }
     excl[j] = 0;
@@ -173,14 +179,14 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_pass(const KeyT* __restri
     }
   }
 #pragma unroll
-  for (int j = 0; j < J; j++) digit_base[tid * J + j] = gstart[j] + excl[j];
+  for (int j = 0; j < J; j++) sm.digit_base[tid * J + j] = gstart[j] + excl[j];
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < kSortItems; r++) {
     const long long idx = base + r * 32 + lane;
     if (idx < n) {
       const unsigned d = (unsigned)((key[r] >> shift) & (KeyT)(kSortBins - 1));
-      const unsigned pos = digit_base[d] + warp_cnt[w][d] + rank[r];
+      const unsigned pos = sm.digit_base[d] + sm.warp_cnt[w][d] + rank[r];
       kout[pos] = key[r];
       vout[pos] = val[r];
       if (out4) {
@@ -190,6 +196,17 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_pass(const KeyT* __restri
       }
     }
   }
+}
+
+// stand-alone pass: one block per tile, tiles in ticket order
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads) k_sort_pass(const KeyT* __restrict__ kin, const unsigned* __restrict__ vin, KeyT* __restrict__ kout, unsigned* __restrict__ vout, int n,
+                                                            int pass, const unsigned* __restrict__ hist, unsigned* state, unsigned* ticket, const float4* __restrict__ in4,
+                                                            float4* __restrict__ out4) {
+  __shared__ SortTileSmem sm;
+  if (threadIdx.x == 0) sm.tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  sort_pass_tile<KeyT>(sm, sm.tile, kin, vin, kout, vout, n, pass, hist, state, in4, out4);
 }
 
 // Sorts n pairs by the low `key_bits` bits of the keys.  (k0, v0) holds the input keys (the values are the positions 0..n-1, v0 is

@@ -707,7 +707,12 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_knn_search(GridArgs a, in
       v[u] = 0xFFFFFFFFu;
       if (p < a.n) v[u] = __float_as_uint(knn_d2(q, __ldg(&a.sorted[p])));
     }
-    T = warp_tighten<2>(v, k, k + (k >> 2) + 1, 0x7f800000u);
+    // bracket: the largest window distance qualifies (>= k valid points); most of the steps of a bisection from [0, inf) would only
+    // locate its binade
+    unsigned mx = max(v[0] == 0xFFFFFFFFu ? 0u : v[0], v[1] == 0xFFFFFFFFu ? 0u : v[1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    T = warp_tighten<2>(v, k, k + 2, mx);
   }
   const int l_min = *a.l_min;
   float s;
@@ -951,7 +956,7 @@ __device__ __forceinline__ void scan_run_strided(WarpTopK& t, int k, int lane, f
   }
 }
 
-constexpr int kKnnGridWarps = 8;  // warps per block of the cooperative kernel
+constexpr int kKnnGridWarps = 16;  // warps per block of the cooperative kernel (a whole-cloud item is 17 k .. 1 M candidates)
 
 // Block-cooperative continuation for the deferred queries: the 8 warps of a block split the candidates of one query -- the runs
 // of the 27 cells of its block at the recorded level, or the whole cloud -- each keeps its own sorted top-k, warp 0 merges the
@@ -1098,10 +1103,10 @@ cudaError_t launch_knn_grid(const float4* pts, int n, int k, int* nbr, unsigned 
   a.codes = codes0;
   if (sorted_out) *sorted_out = a.sorted;
   cudaError_t e;
-  if ((e = cudaMemsetAsync(ff_begin, 0xFF, ff_bytes, stream)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(z_begin, 0, z_bytes, stream)) != cudaSuccess) return e;
   int nl = 0;
   const int nb = (n + 255) / 256;
+  if ((e = cudaMemsetAsync(ff_begin, 0xFF, ff_bytes, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(z_begin, 0, z_bytes, stream)) != cudaSuccess) return e;
   k_grid_bbox<<<nb < 592 ? nb : 592, 256, 0, stream>>>(pts, n, a.bbox_min, a.bbox_max);
   k_grid_codes<<<nb < 1184 ? nb : 1184, kSortThreads, 0, stream>>>(a, passes, reinterpret_cast<unsigned*>(sort_scratch));
   nl += 2;

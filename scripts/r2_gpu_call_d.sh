@@ -1,7 +1,6 @@
 #!/bin/bash
-# ncu --set full of the k-NN search kernel (17k fixture cloud)
+# ncu --set full of the k-NN stage kernels (17k fixture cloud)
 set -u
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_knn_search -s 3 -c 1 -f -o gpurun_out/r2d_knn_search python scripts/exp_knn.py 3 > gpurun_out/r2d_ncu.log 2>&1
-tail -3 gpurun_out/r2d_ncu.log
-ls -la gpurun_out/*.ncu-rep | tail -2
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_knn_search|k_knn_deferred|k_sort_pass|k_grid_table" -s 12 -c 6 -f -o gpurun_out/r2d_knn python scripts/exp_knn.py 3 > gpurun_out/r2d_ncu.log 2>&1
+tail -2 gpurun_out/r2d_ncu.log
