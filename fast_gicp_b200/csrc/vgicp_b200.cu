@@ -154,6 +154,7 @@ struct vgicp_context {
   int align_mode = 1;  // 1 = host-driven loop over the evaluation kernels (default: faster today), 0 = device-resident LM chain
   LmState* d_lm = nullptr;
   LmState* h_lm = nullptr;  // pinned
+  int lin_stream = 1;   // VGICP_LIN_STREAM=0 disables the bulk-copy streaming kernel of DIRECT1 (A/B measurements)
   int force_lin_g = 0;  // VGICP_LIN_G override of the lanes-per-point split (experiments)
   int knn_mode = 0;  // 0 = hash grid (default), 1 = warp-cooperative scan of the whole cloud, 2 = legacy per-thread scan
   DevBuf<double> partials;
@@ -658,6 +659,16 @@ int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H, bool direct
     else LAUNCH_LIN_G(MODE, 1);          \
   } while (0)
   prof_begin(h, want_H ? VGICP_PROF_LINEARIZE : VGICP_PROF_ERROR, h->stream);
+  // DIRECT1 on a large cloud with the direct-mapped index: the bandwidth-bound shape, streamed through shared memory by bulk copies
+  const bool stream_kernel = h->offset_mode == 1 && a.dense.cells != nullptr && a.n >= 65536 && h->lin_stream != 0 && (reinterpret_cast<uintptr_t>(a.covB) & 15) == 0;
+  if (stream_kernel) {
+    const int tiles = (a.n + kLinStreamTile - 1) / kLinStreamTile;
+    const int sgrid = tiles < kLinStreamMaxBlocks ? tiles : kLinStreamMaxBlocks;
+    const size_t smem = sizeof(LinStreamSmem);
+    if (spec) k_linearize_stream<2><<<sgrid, kLinThreads, smem, h->stream>>>(a);
+    else if (want_H) k_linearize_stream<1><<<sgrid, kLinThreads, smem, h->stream>>>(a);
+    else k_linearize_stream<0><<<sgrid, kLinThreads, smem, h->stream>>>(a);
+  } else
   switch (h->offset_mode) {
     case 1: LAUNCH_LIN_G(1, 1); break;
     case 7: LAUNCH_LIN(7); break;
@@ -840,6 +851,7 @@ int vgicp_create(int device, vgicp_handle* out) {
   if (!h) return VGICP_ERR_CUDA;
   h->device = device;
   { const char* e = getenv("VGICP_LIN_G"); h->force_lin_g = e ? atoi(e) : 0; }
+  { const char* e = getenv("VGICP_LIN_STREAM"); h->lin_stream = e ? atoi(e) : 1; }
   DeviceGuard g(device);
   // the kernel image is sm_100a only: fail loudly on anything else instead of falling back
   cudaFuncAttributes fa;
@@ -869,7 +881,7 @@ int vgicp_create(int device, vgicp_handle* out) {
   if (ok) *h->h_flag = 0;
   ok = ok && cudaMalloc(&h->d_lm, sizeof(LmState)) == cudaSuccess;
   ok = ok && cudaMallocHost(&h->h_lm, sizeof(LmState)) == cudaSuccess;
-  ok = ok && h->partials.reserve((size_t)kLinMaxBlocks * kLinStride) == cudaSuccess;
+  ok = ok && h->partials.reserve((size_t)kLinStreamMaxBlocks * kLinStride) == cudaSuccess;
   ok = ok && cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
   if (!ok) {
@@ -1489,11 +1501,12 @@ int vgicp_comm_export_arena(vgicp_handle h, size_t max_points, unsigned char* ha
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
   if (!handle64 || max_points == 0 || max_points > ((size_t)1 << 28)) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "comm_export_arena: bad argument");
+  max_points = (max_points + 15) & ~(size_t)15;  // the two clouds' float4 / float2 arrays follow each other: keep every array 16-byte aligned
   if (h->arena && h->arena_points != max_points) return fail(h, VGICP_ERR_BAD_STATE, "comm_export_arena: arena already allocated with another capacity");
   if (!h->arena) {
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream_b));
-    const size_t bytes = kCommArenaHeaderBytes + 2 * max_points * 24;
+    const size_t bytes = kCommArenaHeaderBytes + 2 * max_points * 24 + 64;  // (+ padding: bulk copies read covB in 16-byte units)
     CU_TRY(h, cudaMalloc(&h->arena, bytes));
     CU_TRY(h, cudaMemset(h->arena, 0, bytes));
     h->arena_points = max_points;

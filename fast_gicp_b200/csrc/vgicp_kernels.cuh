@@ -704,6 +704,9 @@ __device__ __forceinline__ void lin_accumulate(const LinArgs& a, const Pose& Tl,
 
 // block reduction (warp shuffles in float -> shared in double -> per-block partial), ticket, fixed-order fold by the last
 // block.  Returns true in every thread of the last block; the folded sums are then in fin[0][0..NV).
+// (Tried in round 2 and dropped: a first-level reduction over distributed shared memory inside 8-block clusters, so that the last
+// block folds grid/8 partials.  It bought 0.4 us of the 22.6 us of an evaluation at 17 k points and cost 16 % at 1 M points, where the
+// cluster placement constraint left SMs idle at the tail of the single wave.)
 template <int NV>
 __device__ __forceinline__ bool lin_reduce(const LinArgs& a, const float* sum, double (*fin)[kLinStride]) {
   // ---- block reduction: warp shuffles (float) -> shared (double) -> per-block partial ----
@@ -862,6 +865,154 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize_spec(const LinArgs a)
   if (threadIdx.x == 0) {
     lin_unpack<true>(fin[0], a.out);
     a.out[43] = fin[0][kLinValues];
+    *a.ticket = 0u;
+    if (a.done_flag) {
+      __threadfence_system();
+      *a.done_flag = a.done_seq;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// DIRECT1 on large clouds: the bandwidth-bound shape of the evaluation (one lookup and at most one correspondence per point: about
+// 150 instructions against 40 bytes of point + covariance).  The source is streamed through shared memory with the bulk-copy engine:
+// an elected thread issues cp.async.bulk (global -> shared, completion counted on an mbarrier) for the point, covA and covB slices
+// of the tile kLinStreamStages - 1 tiles ahead, so that the HBM reads of later tiles are in flight while the warps chase the
+// dependent loads of the current one (cell index -> voxel record).  No hit compaction: a lane keeps its own point.
+// SPEC: error over the correspondences of Tlin at Teval (sum[28]) and the full linearisation at Teval (sums 0..27) from one pass
+// over the staged points, like k_linearize_spec.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kLinStreamTile = 128;     // points per tile (1 per thread)
+constexpr int kLinStreamStages = 4;
+constexpr int kLinStreamMaxBlocks = 1184;  // 8 x 148 SMs
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+struct LinStreamSmem {
+  float4 pts[kLinStreamStages][kLinStreamTile];
+  float4 covA[kLinStreamStages][kLinStreamTile];
+  float2 covB[kLinStreamStages][kLinStreamTile];
+  unsigned long long full[kLinStreamStages];
+};
+
+// one point against the voxel of its cell under the linearisation pose Tl, residual at the evaluation pose Te
+template <bool WANT_H>
+__device__ __forceinline__ void lin_stream_point(const LinArgs& a, const Pose& Tl, const Pose& Te, float4 p, float4 ca, float2 cb, float* sum) {
+  const float3 pl = transform_point(Tl, p.x, p.y, p.z);
+  const int off = dense_offset(a.dense, voxel_coord1(pl.x, a.res), voxel_coord1(pl.y, a.res), voxel_coord1(pl.z, a.res));
+  const int id = off >= 0 ? __ldg(&a.dense.cells[off]) : -1;
+  if (id < 0) return;
+  const float4* vr = reinterpret_cast<const float4*>(a.vox + id);
+  const float4 mn = __ldg(vr), c0 = __ldg(vr + 1), c1 = __ldg(vr + 2);
+  const float3 pe = transform_point(Te, p.x, p.y, p.z);
+  const float* R = Tl.r;
+  float t[9], rcr[6];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    t[r * 3 + 0] = (R[r * 3] * ca.x + R[r * 3 + 1] * ca.y) + R[r * 3 + 2] * ca.z;
+    t[r * 3 + 1] = (R[r * 3] * ca.y + R[r * 3 + 1] * ca.w) + R[r * 3 + 2] * cb.x;
+    t[r * 3 + 2] = (R[r * 3] * ca.z + R[r * 3 + 1] * cb.x) + R[r * 3 + 2] * cb.y;
+  }
+  rcr[0] = (t[0] * R[0] + t[1] * R[1]) + t[2] * R[2];
+  rcr[1] = (t[0] * R[3] + t[1] * R[4]) + t[2] * R[5];
+  rcr[2] = (t[0] * R[6] + t[1] * R[7]) + t[2] * R[8];
+  rcr[3] = (t[3] * R[3] + t[4] * R[4]) + t[5] * R[5];
+  rcr[4] = (t[3] * R[6] + t[4] * R[7]) + t[5] * R[8];
+  rcr[5] = (t[6] * R[6] + t[7] * R[7]) + t[8] * R[8];
+  PointAcc<WANT_H> acc;
+#pragma unroll
+  for (int q = 0; q < 6; q++) acc.m[q] = 0.f;
+  acc.v[0] = acc.v[1] = acc.v[2] = 0.f;
+  acc.err = 0.f;
+  accumulate_voxel<WANT_H>(mn, c0, c1, true, rcr, pe, acc, a.ndt, a.res);
+  apply_jacobian<WANT_H>(pe, acc, sum);
+}
+
+// WHAT: 0 = error only, 1 = linearisation (H, b, err), 2 = speculative (both)
+template <int WHAT>
+__global__ void __launch_bounds__(kLinThreads) k_linearize_stream(const LinArgs a) {
+  constexpr int NV = WHAT == 0 ? 1 : (WHAT == 1 ? kLinValues : kLinValues + 1);
+  extern __shared__ __align__(128) unsigned char stream_smem_raw[];
+  LinStreamSmem& sm = *reinterpret_cast<LinStreamSmem*>(stream_smem_raw);
+  __shared__ double fin[4][kLinStride];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kLinStreamStages; s++) mbar_init(&sm.full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int n_tiles = (a.n + kLinStreamTile - 1) / kLinStreamTile;
+  auto issue = [&](int it) {  // tile number it of this block -> stage it % kLinStreamStages
+    const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+    if (tile >= n_tiles) return;
+    const int s = it % kLinStreamStages;
+    const int first = (int)tile * kLinStreamTile;
+    const int cnt = min(kLinStreamTile, a.n - first);
+    const int cnt2 = (cnt + 1) & ~1;  // covB is 8 bytes per point: whole 16-byte units (the arrays are padded by at least one element)
+    mbar_expect_tx(&sm.full[s], (unsigned)(cnt * 32 + cnt2 * 8));
+    bulk_copy_g2s(sm.pts[s], a.pts + first, (unsigned)cnt * 16u, &sm.full[s]);
+    bulk_copy_g2s(sm.covA[s], a.covA + first, (unsigned)cnt * 16u, &sm.full[s]);
+    bulk_copy_g2s(sm.covB[s], a.covB + first, (unsigned)cnt2 * 8u, &sm.full[s]);
+  };
+  if (tid == 0)
+    for (int it = 0; it < kLinStreamStages - 1; it++) issue(it);
+  float sum[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) sum[i] = 0.f;
+  for (int it = 0;; it++) {
+    const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+    if (tile >= n_tiles) break;
+    const int s = it % kLinStreamStages;
+    if (tid == 0) issue(it + kLinStreamStages - 1);  // refills the stage read in iteration it - 1 (all threads are past its barrier)
+    mbar_wait(&sm.full[s], (unsigned)((it / kLinStreamStages) & 1));
+    const int first = (int)tile * kLinStreamTile;
+#pragma unroll
+    for (int u = 0; u < kLinStreamTile / kLinThreads; u++) {
+      const int j = u * kLinThreads + tid;
+      if (first + j < a.n) {
+        const float4 p = sm.pts[s][j], ca = sm.covA[s][j];
+        const float2 cb = sm.covB[s][j];
+        if (WHAT == 0) {
+          lin_stream_point<false>(a, a.Tlin, a.Teval, p, ca, cb, sum);
+        } else if (WHAT == 1) {
+          lin_stream_point<true>(a, a.Tlin, a.Teval, p, ca, cb, sum);
+        } else {
+          lin_stream_point<false>(a, a.Tlin, a.Teval, p, ca, cb, sum + kLinValues);
+          lin_stream_point<true>(a, a.Teval, a.Teval, p, ca, cb, sum);
+        }
+      }
+    }
+    __syncthreads();  // the stage may be overwritten by the copy issued in the next iteration
+  }
+  if (!lin_reduce<NV>(a, sum, fin)) return;
+  if (tid == 0) {
+    if (WHAT == 0) {
+      lin_unpack<false>(fin[0], a.out);
+    } else {
+      lin_unpack<true>(fin[0], a.out);
+      if (WHAT == 2) a.out[43] = fin[0][kLinValues];
+    }
     *a.ticket = 0u;
     if (a.done_flag) {
       __threadfence_system();

@@ -1,6 +1,7 @@
 #!/bin/bash
-# ncu --set full of the k-NN stage kernels (17k fixture cloud)
+# ncu --set full of the evaluation kernels at 1M points (stream kernel, DIRECT27) 
 set -u
 mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_knn_search|k_knn_deferred|k_sort_pass|k_grid_table" -s 12 -c 6 -f -o gpurun_out/r2d_knn python scripts/exp_knn.py 3 > gpurun_out/r2d_ncu.log 2>&1
+timeout 300 python scripts/exp_eval_c4.py 20 2>&1 | tail -2
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_linearize" -s 4 -c 4 -f -o gpurun_out/r2d_eval python scripts/exp_eval_c4.py 2 > gpurun_out/r2d_ncu.log 2>&1
 tail -2 gpurun_out/r2d_ncu.log

@@ -25,6 +25,14 @@ far = np.vstack([tgt, np.array([[3.0e6, -2.0e6, 1.0e6]], dtype=np.float32)])
 r = c.register(far, src)
 print("outlier", "converged", bool(r.converged))
 c.close()
+# DIRECT1 on a cloud above the streaming threshold: k_linearize_stream (bulk copies into shared memory, mbarriers), 1M-class sort path
+from fast_gicp_b200.synthetic import kitti_like_pair
+bt, bs, _ = kitti_like_pair(beams=48, az_steps=2083, seed=5, pose=(0.4, 0.05, 0.5), downsample=0.0)
+c = Core(0)
+c.set_resolution(0.5); c.set_neighbor_search_method("DIRECT1")
+r = c.register(bt, bs)
+print("stream", len(bs), "converged", bool(r.converged))
+c.close()
 # NDT D2D through the same evaluation kernels
 c = Core(0)
 c.set_problem(2); c.set_neighbor_search_method("DIRECT7")

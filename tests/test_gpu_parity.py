@@ -594,6 +594,44 @@ def test_c4_matches_the_oracle_golden():
     c.close()
 
 
+def test_direct1_streaming_kernel_matches_the_gather_kernel():
+    """DIRECT1 evaluations of clouds >= 64k points run in k_linearize_stream (source staged through shared memory by bulk copies);
+    VGICP_LIN_STREAM=0 keeps the ordinary kernel.  Same correspondences, same per-term arithmetic, another summation order: err, H, b
+    agree to float rounding, the registration walks the same iterates, and both match the oracle."""
+    import os
+
+    from fast_gicp_b200.core import Core, pose_from_c
+    from fast_gicp_b200.synthetic import kitti_like_pair
+
+    tgt, src, T_gt = kitti_like_pair(beams=64, az_steps=2083, seed=7, pose=(0.6, 0.1, 0.8), downsample=0.0)
+    assert len(src) > 65536
+    got = {}
+    for flag in ("1", "0"):
+        os.environ["VGICP_LIN_STREAM"] = flag
+        c = Core(0)
+        os.environ.pop("VGICP_LIN_STREAM")
+        _setup_pair(c, dict(tgt=tgt, src=src), O.DIRECT1, res=0.5)
+        rows = []
+        for T in (np.eye(4), T_gt):
+            c.update_correspondences(T)
+            rows.append(c.compute_error(T, True) + c.compute_error(T, False)[:1])
+        res = c.align()
+        got[flag] = (rows, pose_from_c(res.T), res.nr_iterations, res.n_linearize, res.n_compute_error, bool(res.converged))
+        if flag == "1":
+            cov_t, cov_s = c.get_target_covariances(), c.get_source_covariances()
+        c.close()
+    for (e1, H1, b1, eo1), (e0, H0, b0, eo0) in zip(got["1"][0], got["0"][0]):
+        assert abs(e1 - e0) <= 2e-6 * abs(e0) and abs(eo1 - eo0) <= 2e-6 * abs(eo0)
+        assert np.abs(H1 - H0).max() <= 2e-6 * np.abs(H0).max() and np.abs(b1 - b0).max() <= 2e-6 * max(np.abs(b0).max(), 1e-3 * np.abs(H0).max())
+    assert got["1"][2:] == got["0"][2:] and got["1"][5]
+    dt, dr = pose_error(got["0"][1], got["1"][1])
+    assert dt < 1e-6 and dr < 1e-7, (dt, dr)
+    vm = O.VoxelMap(tgt, cov_t, 0.5, accum_double=True)
+    e0, H0, b0, _ = O.evaluate(vm, src, cov_s, O.offsets(O.DIRECT1), T_gt, T_gt, True)
+    e1, H1, b1, _ = got["1"][0][1]
+    assert abs(e1 - e0) <= 2e-5 * abs(e0) and np.abs(H1 - H0).max() <= 2e-5 * np.abs(H0).max()
+
+
 def _rbf_cloud():
     rng = np.random.default_rng(2)
     pts = (rng.normal(size=(1500, 3)) * [3.0, 3.0, 0.2]).astype(np.float32)
