@@ -77,7 +77,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -339,6 +339,9 @@ def c4_record(torch, dev, local_rank, rank, world, peak_gbs, note):
         sh = {}
         c2 = Core(local_rank)
         c2.set_resolution(0.5)
+        # device-resident LM chain: the optimiser's state machine runs in the last block of each evaluation kernel, after the in-kernel
+        # exchange, so the ranks stay in lock-step without a host round trip (and its launch skew) per evaluation
+        c2.set_align_mode(0)
         lo, hi = D.setup_source_sharding(c2, n_s, max_points=max(n_s, n_t))
         for method in ("DIRECT27", "DIRECT1"):
             c2.set_neighbor_search_method(method)

@@ -108,6 +108,7 @@ def build_host_cpp(force=False):
     import pybind11
 
     build_native(force=False)
+    build_prep(force=False)  # pygicp's downsample / align_points run the device-side ApproximateVoxelGrid
     cpp = os.path.join(HERE, "cpp")
     inc = os.path.join(cpp, "include")
     ext = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
@@ -115,7 +116,8 @@ def build_host_cpp(force=False):
     exe = os.path.join(LIB_DIR, "gicp_test")
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-    hdrs = [os.path.join(inc, "fast_gicp_b200", f) for f in os.listdir(os.path.join(inc, "fast_gicp_b200"))] + [os.path.join(ROOT, "include", "vgicp_b200.h"), LIB_PATH]
+    hdrs = [os.path.join(inc, "fast_gicp_b200", f) for f in os.listdir(os.path.join(inc, "fast_gicp_b200"))] + [os.path.join(ROOT, "include", "vgicp_b200.h"),
+                                                                                                                 os.path.join(ROOT, "include", "vgicp_prep_b200.h"), LIB_PATH]
 
     def stale(out, srcs):
         return force or not os.path.exists(out) or any(os.path.getmtime(x) > os.path.getmtime(out) for x in srcs + hdrs)
@@ -123,8 +125,8 @@ def build_host_cpp(force=False):
     common = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-I", inc, "-L", LIB_DIR, "-Wl,-rpath,$ORIGIN"]
     src_mod = os.path.join(cpp, "pygicp_module.cpp")
     if stale(mod, [src_mod]):
-        subprocess.check_call([gxx, "-shared", "-fvisibility=hidden", src_mod, "-o", mod, "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"]] + common + ["-lvgicp_b200"],
-                              env=env)
+        subprocess.check_call([gxx, "-shared", "-fvisibility=hidden", src_mod, "-o", mod, "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"]] + common +
+                              ["-lvgicp_b200", "-lvgicp_prep_b200"], env=env)
     src_test = os.path.join(ROOT, "tests", "cpp", "gicp_test.cpp")
     if stale(exe, [src_test]):
         subprocess.check_call([gxx, src_test, "-o", exe] + common + ["-lvgicp_b200"], env=env)

@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "vgicp_set_source_cloud_device", "vgicp_set_target_cloud_device", "vgicp_set_profiling", "vgicp_get_profile", "vgicp_profile_category_name",
     "vgicp_set_knn_mode", "vgicp_set_voxel_index", "vgicp_set_speculation", "vgicp_register", "vgicp_set_align_mode", "vgicp_get_fitness_score", "vgicp_set_execution_hint", "vgicp_set_problem", "vgicp_ndt_create_voxelmaps",
     "vgicp_comm_export", "vgicp_comm_init", "vgicp_comm_shutdown", "vgicp_comm_error", "vgicp_set_source_shard", "vgicp_clear_source_shard",
-    "vgicp_comm_export_arena", "vgicp_comm_init_arena", "vgicp_set_stage1_sharding",
+    "vgicp_comm_export_arena", "vgicp_comm_init_arena", "vgicp_set_stage1_sharding", "vgicp_set_source_covariances", "vgicp_set_target_covariances",
 ]
 PROF_NUM_CATEGORIES = 7
 
@@ -142,6 +142,8 @@ def load_library():
         "vgicp_comm_export_arena": [hp, C.c_size_t, C.c_void_p],
         "vgicp_comm_init_arena": [hp, C.c_void_p],
         "vgicp_set_stage1_sharding": [hp, C.c_int],
+        "vgicp_set_source_covariances": [hp, fp, C.c_size_t],
+        "vgicp_set_target_covariances": [hp, fp, C.c_size_t],
         "vgicp_register": [hp, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, dp, C.POINTER(LsqParams), C.POINTER(AlignResult)],
         "vgicp_get_profile": [hp, dp, C.POINTER(C.c_uint64), C.c_int],
     }
@@ -310,6 +312,15 @@ class Core:
 
     def calculate_target_covariances_rbf(self, method=REG_PLANE):
         return self._check(self._lib.vgicp_calculate_target_covariances_rbf(self._h, int(method)), allow=(ERR_UNSUPPORTED,))
+
+    def set_source_covariances(self, cov9):
+        """(n, 9) or (n, 3, 3) float32, column-major 3x3 per point (== get_source_covariances())."""
+        c = np.ascontiguousarray(np.asarray(cov9, dtype=np.float32).reshape(-1, 9))
+        self._check(self._lib.vgicp_set_source_covariances(self._h, c.ctypes.data_as(C.POINTER(C.c_float)), len(c)))
+
+    def set_target_covariances(self, cov9):
+        c = np.ascontiguousarray(np.asarray(cov9, dtype=np.float32).reshape(-1, 9))
+        self._check(self._lib.vgicp_set_target_covariances(self._h, c.ctypes.data_as(C.POINTER(C.c_float)), len(c)))
 
     def num_source_points(self):
         n = C.c_size_t(0)

@@ -12,6 +12,8 @@
 #include <fast_gicp_b200/fast_vgicp_cuda.hpp>
 #include <fast_gicp_b200/ndt_cuda.hpp>
 
+#include "../../include/vgicp_prep_b200.h"
+
 namespace py = pybind11;
 using Cloud = pcl::PointCloud<pcl::PointXYZ>;
 using LsqReg = fast_gicp::LsqRegistration<pcl::PointXYZ, pcl::PointXYZ>;
@@ -42,27 +44,22 @@ static Cloud::Ptr eigen2pcl(const ArrD& points) {  // main.cpp:36-44 (double -> 
   return cloud;
 }
 
-// pcl::ApproximateVoxelGrid<PointXYZ>::applyFilter restated (512-entry hash history, flush on collision); pinned by the
-// point counts of README.md:116 (tests/golden/make_fixtures.py holds the same algorithm in numpy)
+// pcl::ApproximateVoxelGrid<PointXYZ> (main.cpp:46-62,81-91) on the device: include/vgicp_prep_b200.h reproduces the serial
+// filter's output (points and order) bit for bit (tests/test_input_prep.py); no host implementation is kept in the product.
 static Cloud::Ptr approximate_voxel_grid(const Cloud& in, float leaf) {
-  struct He { int ix = 0, iy = 0, iz = 0, count = 0; float sx = 0, sy = 0, sz = 0; };
-  const int histsize = 512;
-  std::vector<He> hist(histsize);
+  static vgicp_prep_handle prep = nullptr;  // one per process, device 0 like the registration objects' default
+  if (!prep && vgicp_prep_create(0, &prep) != 0) throw std::runtime_error("pygicp: the input-preparation library found no usable CUDA device (sm_100a required)");
   auto out = pcl::make_shared<Cloud>();
-  const float inv = 1.0f / leaf;
-  auto flush = [&](He& h) {
-    out->push_back(pcl::PointXYZ(h.sx / h.count, h.sy / h.count, h.sz / h.count));
-    h.count = 0; h.sx = h.sy = h.sz = 0;
-  };
-  for (const auto& p : in.points) {
-    int ix = static_cast<int>(std::floor(p.x * inv)), iy = static_cast<int>(std::floor(p.y * inv)), iz = static_cast<int>(std::floor(p.z * inv));
-    He& h = hist[static_cast<unsigned>(ix * 7171 + iy * 3079 + iz * 4231) & (histsize - 1)];
-    if (h.count && (ix != h.ix || iy != h.iy || iz != h.iz)) flush(h);
-    h.ix = ix; h.iy = iy; h.iz = iz;
-    h.count++;
-    h.sx += p.x; h.sy += p.y; h.sz += p.z;
-  }
-  for (auto& h : hist) if (h.count) flush(h);
+  const size_t n = in.points.size();
+  if (n == 0) return out;
+  out->points.resize(n);
+  size_t m = 0;
+  static_assert(sizeof(pcl::PointXYZ) % 4 == 0, "point stride");
+  std::vector<float> packed(3 * n);
+  const int rc = vgicp_prep_approximate_voxel_grid(prep, &in.points[0].x, n, sizeof(pcl::PointXYZ), 0, leaf, 0, packed.data(), n, 0, &m);
+  if (rc != 0) throw std::runtime_error(std::string("pygicp.downsample: ") + vgicp_prep_last_error(prep));
+  out->points.resize(m);
+  for (size_t i = 0; i < m; i++) out->points[i] = pcl::PointXYZ(packed[3 * i], packed[3 * i + 1], packed[3 * i + 2]);
   return out;
 }
 

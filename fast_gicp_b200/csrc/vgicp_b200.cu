@@ -414,6 +414,28 @@ int get_covariances(vgicp_handle h, Cloud& c, float* out9, size_t cap) {
   return VGICP_OK;
 }
 
+int set_covariances(vgicp_handle h, Cloud& c, const float* in9, size_t n) {
+  if (!c.has_pts) return fail(h, VGICP_ERR_BAD_STATE, "set_covariances: cloud not set");
+  if (!in9 || n != (size_t)c.n) return fail(h, VGICP_ERR_INVALID_ARGUMENT, "set_covariances: need one 3x3 per point of the cloud");
+  CU_TRY(h, c.covA.reserve(c.n));
+  CU_TRY(h, c.covB.reserve(c.n));
+  std::vector<float4> a(c.n);
+  std::vector<float2> b(c.n);
+  for (int i = 0; i < c.n; i++) {  // column-major in, symmetric-packed out (the mean of the two triangles, like the kernels)
+    const float* m = in9 + (size_t)i * 9;
+    a[i] = make_float4(m[0], 0.5f * (m[1] + m[3]), 0.5f * (m[2] + m[6]), m[4]);
+    b[i] = make_float2(0.5f * (m[5] + m[7]), m[8]);
+  }
+  if (c.n) {
+    CU_TRY(h, cudaMemcpyAsync(c.covA.p, a.data(), sizeof(float4) * c.n, cudaMemcpyHostToDevice, c.st));
+    CU_TRY(h, cudaMemcpyAsync(c.covB.p, b.data(), sizeof(float2) * c.n, cudaMemcpyHostToDevice, c.st));
+    CU_TRY(h, cudaStreamSynchronize(c.st));
+  }
+  c.has_cov = true;
+  CU_TRY(h, cudaEventRecord(c.ready, c.st));
+  return VGICP_OK;
+}
+
 int get_neighbors(vgicp_handle h, Cloud& c, int* out, size_t cap, int* k_out) {
   if (c.k <= 0) return fail(h, VGICP_ERR_BAD_STATE, "get_neighbors: neighbours not set");
   if (k_out) *k_out = c.k;
@@ -431,18 +453,29 @@ int get_neighbors(vgicp_handle h, Cloud& c, int* out, size_t cap, int* k_out) {
 //   voxelmap_begin  enqueues coordinates + the first insertion attempt (8192 buckets) + the read-back of its failure count
 //   voxelmap_finish (called by whoever needs the map) waits for that count, grows the table if the reference would
 //                   (:265-285), then ids / accumulate / finalize.  num_voxels itself is fetched lazily.
-int voxelmap_attempt(vgicp_handle h, Cloud& t, VoxelMap& m, int B) {
+// One or more table attempts (B, 2B, 4B, ...) enqueued back to back; k_table_verdict records the first size that meets the
+// reference's rule and the kernels of the later attempts see it and return, so the outcome is that of the reference's sequential
+// doubling with one host synchronisation instead of one per attempt (large clouds need 3: 8192 -> 32768 buckets at 1 M points).
+int voxelmap_attempt(vgicp_handle h, Cloud& t, VoxelMap& m, int B, int count) {
   const int n = t.n;
-  CU_TRY(h, m.slots.reserve(B));
-  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_fill_i32<<<blocks_for(B, 256), 256, 0, t.st>>>(m.slots.p, -1, (size_t)B));
-  CU_TRY(h, cudaMemsetAsync(m.d_counters, 0, 2 * sizeof(int), t.st));
-  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_table_insert<<<blocks_for(n, 256), 256, 0, t.st>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan));
-  KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP,
-             k_table_lookup_points<<<blocks_for(n, 256), 256, 0, t.st>>>(m.coords.p, n, m.slots.p, (unsigned)(B - 1), m.max_scan, m.slot_of_point.p, m.d_counters));
+  int B_last = B;
+  for (int j = 1; j < count && B_last < (1 << 28); j++) B_last *= 2;
+  CU_TRY(h, m.slots.reserve(B_last));
+  int* skip = m.d_counters + 9;
+  CU_TRY(h, cudaMemsetAsync(skip, 0, sizeof(int), t.st));
+  int Bj = B;
+  for (int j = 0; j < count && Bj <= B_last; j++, Bj *= 2) {
+    CU_TRY(h, cudaMemsetAsync(m.d_counters, 0, sizeof(int), t.st));
+    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_fill_i32<<<blocks_for(Bj, 256), 256, 0, t.st>>>(m.slots.p, -1, (size_t)Bj, skip));
+    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_table_insert<<<blocks_for(n, 256), 256, 0, t.st>>>(m.coords.p, n, m.slots.p, (unsigned)(Bj - 1), m.max_scan, skip));
+    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP,
+               k_table_lookup_points<<<blocks_for(n, 256), 256, 0, t.st>>>(m.coords.p, n, m.slots.p, (unsigned)(Bj - 1), m.max_scan, m.slot_of_point.p, m.d_counters, skip));
+    KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_table_verdict<<<1, 1, 0, t.st>>>(m.d_counters, n, Bj));
+  }
   CU_TRY(h, cudaGetLastError());
-  CU_TRY(h, cudaMemcpyAsync(m.h_counters, m.d_counters, sizeof(int), cudaMemcpyDeviceToHost, t.st));
+  CU_TRY(h, cudaMemcpyAsync(m.h_counters + 9, m.d_counters + 9, sizeof(int), cudaMemcpyDeviceToHost, t.st));
   CU_TRY(h, cudaEventRecord(m.ev_attempt, t.st));
-  m.pending_B = B;
+  m.pending_B = B_last;
   return VGICP_OK;
 }
 
@@ -462,7 +495,8 @@ int voxelmap_begin(vgicp_handle h, Cloud& t, VoxelMap& m) {
   CU_TRY(h, cudaMemsetAsync(m.d_counters + 5, 0x80, 3 * sizeof(int), t.st));  // running maximum: starts at 0x80808080
   KLAUNCH_ST(h, t.st, VGICP_PROF_VOXELMAP, k_voxel_coords<<<blocks_for(n, 256), 256, 0, t.st>>>(t.pts.p, n, m.res, m.coords.p, m.d_counters + 2));
   CU_TRY(h, cudaMemcpyAsync(m.h_counters + 2, m.d_counters + 2, 6 * sizeof(int), cudaMemcpyDeviceToHost, t.st));
-  int rc = voxelmap_attempt(h, t, m, m.init_num_buckets);
+  // small clouds pass with the initial 8192 buckets (1082 voxels at 17 k points); large ones are given three sizes to try at once
+  int rc = voxelmap_attempt(h, t, m, m.init_num_buckets, n > 200000 ? 3 : 1);
   if (rc) return rc;
   m.pending = true;
   return VGICP_OK;
@@ -471,13 +505,13 @@ int voxelmap_begin(vgicp_handle h, Cloud& t, VoxelMap& m) {
 int voxelmap_finish(vgicp_handle h, Cloud& t, VoxelMap& m) {
   if (!m.pending) return m.built ? VGICP_OK : fail(h, VGICP_ERR_BAD_STATE, "target voxel map not built");
   const int n = t.n;
-  int B = m.pending_B;
+  int B = 0;
   for (;;) {  // :265 (no upper bound in the reference; bounded here)
     CU_TRY(h, cudaEventSynchronize(m.ev_attempt));
-    if ((double)m.h_counters[0] / (double)n < 0.01) break;  // :280
-    B *= 2;
+    if (m.h_counters[9] != 0) { B = m.h_counters[9]; break; }  // :280, decided on the device
+    B = m.pending_B * 2;
     if (B > (1 << 28)) { m.pending = false; return fail(h, VGICP_ERR_INVALID_ARGUMENT, "create_target_voxelmap: hash table would exceed 2^28 buckets"); }
-    int rc = voxelmap_attempt(h, t, m, B);
+    int rc = voxelmap_attempt(h, t, m, B, 2);
     if (rc) return rc;
   }
   m.pending = false;
@@ -688,7 +722,8 @@ int launch_linearize(vgicp_handle h, const Pose& Teval, bool want_H, bool direct
 
 // one link of the device-resident optimiser chain
 int launch_lm_step(vgicp_handle h, const LinLaunch& L) {
-  const LinArgs& a = L.a;
+  LinArgs a = L.a;
+  a.comm_seq = h->comm_seq++;  // (links that find the chain finished return before the exchange, on every rank alike)
   const int grid = L.grid, G = L.G;
 #define LAUNCH_LM_G(MODE, GG) k_lm_step<MODE, GG><<<grid, kLinThreads, 0, h->stream>>>(a, h->d_lm)
 #define LAUNCH_LM(MODE)                 \
@@ -1074,6 +1109,18 @@ int vgicp_calculate_target_covariances_rbf(vgicp_handle h, int method) {
   DeviceGuard g(h->device);
   return calc_covariances_rbf(h, h->target, method);
 }
+int vgicp_set_source_covariances(vgicp_handle h, const float* in9, size_t n) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  return set_covariances(h, h->source, in9, n);
+}
+int vgicp_set_target_covariances(vgicp_handle h, const float* in9, size_t n) {
+  CHECK_HANDLE(h);
+  DeviceGuard g(h->device);
+  h->map.built = false;  // the voxel Gaussians average the target covariances: the map must be rebuilt (create_target_voxelmap)
+  h->map.pending = false;
+  return set_covariances(h, h->target, in9, n);
+}
 int vgicp_get_source_covariances(vgicp_handle h, float* out9, size_t cap) {
   CHECK_HANDLE(h);
   DeviceGuard g(h->device);
@@ -1278,7 +1325,7 @@ int vgicp_align(vgicp_handle h, const double guess[16], const vgicp_lsq_params* 
   }
   { int rc = sync_inputs(h); if (rc) return rc; }
 
-  if (h->align_mode == 0 && h->comm_ranks <= 1) {
+  if (h->align_mode == 0) {
     // device-resident loop: initialise the state block, enqueue evaluation links, read the state back once per chunk
     LmState* st = h->h_lm;
     memset(st, 0, sizeof(LmState));

@@ -141,9 +141,16 @@ __device__ __forceinline__ int dense_offset(const DenseIndex& d, int x, int y, i
   return (ux < d.nx && uy < d.ny && uz < d.nz) ? (int)((ux * d.ny + uy) * d.nz + uz) : -1;
 }
 
-__global__ void k_fill_i32(int* __restrict__ p, int v, size_t n) {
+// `skip` (may be null): the table attempts of a growth sequence are enqueued back to back; once one of them has met the reference's
+// acceptance rule (*skip != 0, set by k_table_verdict) the kernels of the later, larger attempts return at once
+__global__ void k_fill_i32(int* __restrict__ p, int v, size_t n, const int* __restrict__ skip) {
+  if (skip && *skip) return;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+}
+// gaussian_voxelmap.cu:280: the table is accepted when fewer than 1 % of the points failed to find their voxel
+__global__ void k_table_verdict(int* __restrict__ counters /* [0] failures, [9] accepted table size */, int n, int num_buckets) {
+  if (counters[9] == 0 && (double)counters[0] / (double)n < 0.01) counters[9] = num_buckets;
 }
 
 // after a sharded covariance kernel (stream order): make this rank's peer stores visible, tell every rank that the slice of cloud
@@ -179,7 +186,8 @@ __device__ __forceinline__ bool coord_less(int4 a, int4 b) {
   return a.z < b.z;
 }
 
-__global__ void k_table_insert(const int4* __restrict__ coords, int n, int* slots, unsigned mask, int max_scan) {
+__global__ void k_table_insert(const int4* __restrict__ coords, int n, int* slots, unsigned mask, int max_scan, const int* __restrict__ skip) {
+  if (skip && *skip) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int cur = i;
@@ -211,7 +219,8 @@ __global__ void k_table_insert(const int4* __restrict__ coords, int n, int* slot
 
 // per point: find the slot of its voxel (stop at first empty like find_voxel_correspondences.cu:43-45) and count failures
 __global__ void k_table_lookup_points(const int4* __restrict__ coords, int n, const int* __restrict__ slots, unsigned mask, int max_scan, int* __restrict__ slot_of_point,
-                                      int* __restrict__ fail_counter) {
+                                      int* __restrict__ fail_counter, const int* __restrict__ skip) {
+  if (skip && *skip) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int4 c = coords[i];

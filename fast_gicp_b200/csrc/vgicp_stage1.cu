@@ -677,6 +677,13 @@ __device__ __forceinline__ int level_for(float B, int l_min, int L, float s0, fl
 //      the bound are appended (ballot + prefix) to the warp's buffer in shared memory -- nothing is sorted while scanning;
 //   4. the buffer is tightened to at most 32 (64 for k > 32) keys by another bisection, the survivors are sorted once across the
 //      lanes (bitonic network on 64-bit keys) and the first k are the row, ascending in (d2, index).
+// Measured alternatives (round 2, 17 k-point fixture cloud, B200; all exact, all dropped):
+//   one thread per query, max-heap of the k best in shared memory   592 us  (1530 warp-instructions per query at 37 % lane efficiency,
+//                                                                            dependent shared-memory chains, a 3x tail)
+//   one thread per query, bisection + append buffer + rank sort      608 us
+//   this kernel with four consecutive queries per warp sharing the 27 table lookups      90 us  (fewer, longer warps)
+//   eight lanes per query, four queries per warp (segmented ballots / shuffles)          ~118 us (132 -> 207 us for the whole stage)
+//   this kernel                                                       43 us  (1200 warp-instructions per query, 69 % issue utilisation)
 template <bool WIDE>
 __global__ void __launch_bounds__(kSearchWarps * 32) k_knn_search(GridArgs a, int force_whole_cloud) {
   __shared__ tkey sbuf[kSearchWarps][kWarpBuf];

@@ -93,6 +93,11 @@ VGICP_API int vgicp_calculate_target_covariances_rbf(vgicp_handle h, int regular
 /* get_{source,target}_covariances :245-255 -- out9: n x 9 floats */
 VGICP_API int vgicp_get_source_covariances(vgicp_handle h, float* out9, size_t capacity_points);
 VGICP_API int vgicp_get_target_covariances(vgicp_handle h, float* out9, size_t capacity_points);
+/* Caller-supplied covariances instead of the k-NN ones: the CUDA counterpart of FastGICP::setSourceCovariances /
+ * setTargetCovariances (include/fast_gicp/gicp/fast_gicp.hpp:60-62, CPU classes only in the reference): in9 = n x 9 floats,
+ * column-major 3x3 per point (the layout get_*_covariances returns); the symmetric part is stored.  n must equal the cloud size. */
+VGICP_API int vgicp_set_source_covariances(vgicp_handle h, const float* in9, size_t n_points);
+VGICP_API int vgicp_set_target_covariances(vgicp_handle h, const float* in9, size_t n_points);
 /* public members source_neighbors / target_neighbors (fast_vgicp_cuda.cuh:80-81) read back: n x k ints */
 VGICP_API int vgicp_get_source_neighbors(vgicp_handle h, int* out, size_t capacity_ints, int* k_out);
 VGICP_API int vgicp_get_target_neighbors(vgicp_handle h, int* out, size_t capacity_ints, int* k_out);

@@ -632,6 +632,30 @@ def test_direct1_streaming_kernel_matches_the_gather_kernel():
     assert abs(e1 - e0) <= 2e-5 * abs(e0) and np.abs(H1 - H0).max() <= 2e-5 * np.abs(H0).max()
 
 
+def test_caller_supplied_covariances(prepared, relative_pose):
+    """vgicp_set_{source,target}_covariances (FastGICP::setSourceCovariances / setTargetCovariances on the CUDA path): feeding the
+    oracle's covariances gives the oracle's voxel map and linear system; the size is checked."""
+    from fast_gicp_b200.core import ERR_INVALID_ARGUMENT, Core, VgicpError
+
+    c = Core(0)
+    c.set_neighbor_search_method(O.DIRECT7)
+    c.set_target_cloud(prepared["tgt"])
+    c.set_target_covariances(prepared["t_cov"])
+    c.create_target_voxelmap()
+    c.set_source_cloud(prepared["src"])
+    c.set_source_covariances(prepared["s_cov"])
+    assert np.array_equal(c.get_source_covariances(), sym(prepared["s_cov"]).astype(np.float32))
+    vm = O.VoxelMap(prepared["tgt"], sym(prepared["t_cov"]).astype(np.float32), 1.0, accum_double=True)
+    assert np.array_equal(c.get_voxel_means(), vm.vox_mean) and np.array_equal(c.get_voxel_covs(), vm.vox_cov)
+    err, H, b = c.linearize(relative_pose)
+    e0, H0, b0, _ = O.evaluate(vm, prepared["src"], sym(prepared["s_cov"]).astype(np.float32), O.offsets(O.DIRECT7), relative_pose, relative_pose, True)
+    assert abs(err - e0) <= 2e-5 * abs(e0) and np.abs(H - H0).max() <= 2e-5 * np.abs(H0).max()
+    with pytest.raises(VgicpError) as e:
+        c.set_source_covariances(prepared["s_cov"][:-1])
+    assert e.value.code == ERR_INVALID_ARGUMENT
+    c.close()
+
+
 def _rbf_cloud():
     rng = np.random.default_rng(2)
     pts = (rng.normal(size=(1500, 3)) * [3.0, 3.0, 0.2]).astype(np.float32)

@@ -31,8 +31,10 @@ def test_pygicp_surface():
         assert hasattr(m.FastVGICPCuda, meth), meth
 
 
+@pytest.mark.gpu
 def test_pygicp_downsample_matches_restated_approximate_voxelgrid():
-    """pygicp.downsample (C++) == the numpy restatement that reproduces README.md:116's point counts."""
+    """pygicp.downsample (main.cpp:46-62; runs pcl::ApproximateVoxelGrid on the device through libvgicp_prep_b200.so) == the numpy
+    restatement that reproduces README.md:116's point counts: same points in the same order."""
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     import make_fixtures as mf
 
@@ -41,7 +43,17 @@ def test_pygicp_downsample_matches_restated_approximate_voxelgrid():
     want = mf.approximate_voxel_grid(pts, 0.5)
     got = _pygicp().downsample(pts.astype(np.float64), 0.5)
     assert got.shape == want.shape
-    assert np.abs(got - want.astype(np.float64)).max() < 1e-5
+    assert np.array_equal(got, want.astype(np.float64))
+
+
+def test_pygicp_downsample_without_a_device_fails_loudly():
+    """No host fallback for the input preparation either: without a usable GPU pygicp.downsample raises."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        _pygicp().downsample(np.zeros((10, 3)), 0.5)
 
 
 def test_pygicp_unknown_method_returns_identity(capfd):
