@@ -26,8 +26,12 @@ WANT = {
     "sm__cycles_elapsed.avg": "sm_cycles_elapsed",
     "smsp__issue_active.avg.per_cycle_active": "issue_per_cycle_active",
 }
-CATEGORY = (("k_linearize_spec", "linearize"), ("k_linearize<27, 0", "compute_error"), ("k_linearize<27, 1", "linearize"), ("k_linearize<", "linearize_other"), ("k_knn_grid_heavy", "knn_heavy"), ("k_knn_grid", "knn"),
-            ("k_covariance_knn", "covariance"), ("k_table_insert", "voxelmap_build"))
+# bench.py category -> the kernels whose DRAM bytes add up to one launch of that category (one cloud's k-NN stage, one map build, ...)
+CATEGORY = {"linearize": ("k_linearize_spec",), "compute_error": ("k_linearize<(int)27, (bool)0",),
+            "knn": ("k_grid_bbox", "k_grid_codes", "k_sort_pass<unsigned long long>", "k_grid_levels", "k_grid_table", "k_knn_search", "k_knn_deferred"),
+            "covariance": ("k_covariance_knn",),
+            "voxelmap_build": ("k_voxel_coords", "k_fill_i32", "k_table_insert", "k_table_lookup_points", "k_table_verdict", "k_table_assign_ids", "k_voxel_sort_keys",
+                               "k_sort_pass<unsigned int>", "k_voxel_segments", "k_voxel_reduce")}
 
 
 def main():
@@ -63,14 +67,28 @@ def main():
     for e in summary:
         print(f"{e['kernel'][:60]:60s} x{e['launches']:<3d} {e.get('duration_us', 0):8.1f} us  dram {e['traffic_bytes'] / 1e6:7.2f} MB  instr {e.get('warp_instr', 0) / 1e6:6.2f} M  regs {e.get('regs', 0):4.0f}")
     if len(sys.argv) > 3:
+        # per category: sum over its kernels of (DRAM bytes per launch x launches of that kernel per launch of the category)
+        import hashlib, os
         traffic = {}
-        for e in summary:
-            for pat, cat in CATEGORY:
-                if pat in e["kernel"]:
-                    traffic.setdefault(cat, e["traffic_bytes"])
-                    break
-        traffic["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (cache flushed before each replay), C2 workload single stream; "
-                            "source " + out)
+        for cat, pats in CATEGORY.items():
+            tot, seen = 0.0, False
+            for pat in pats:
+                es = [e for e in summary if pat in e["kernel"]]
+                if not es:
+                    continue
+                seen = True
+                mult = 3.0 if pat.startswith("k_sort_pass<unsigned long long>") else (2.0 if pat.startswith("k_sort_pass<unsigned int>") else 1.0)  # passes per sort
+                tot += mult * sum(e["traffic_bytes"] for e in es) / len(es)
+            if seen:
+                traffic[cat] = tot
+        h = hashlib.sha256()
+        d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fast_gicp_b200", "csrc")
+        for f in sorted(os.listdir(d)):
+            if f.endswith((".cu", ".cuh", ".hpp")):
+                h.update(open(os.path.join(d, f), "rb").read())
+        traffic["source_hash"] = h.hexdigest()[:16]  # bench.py quotes these figures only while the CUDA sources hash to this
+        traffic["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch of a bench.py category (its kernels added up), ncu --set full "
+                            "(caches flushed before each replay), C2 workload single stream; written by scripts/make_traffic.sh from " + out)
         json.dump(traffic, open(sys.argv[3], "w"), indent=1)
 
 
