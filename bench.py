@@ -185,6 +185,18 @@ def run_reference_arm(args, w, rank, world):
         times.append(time.perf_counter() - t0)
     med = float(np.median(times))
     value = 1.0 / med
+    # BASELINE config 1: FastGICP, single thread (fast_gicp_impl.hpp:117-301 restated), same pair; a reported row, not the arm's value
+    config1 = None
+    if w.get("problem") != "ndt_d2d" and len(w["target"]) < 100000:
+        t1 = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            tc = O.covariances_f64(w["target"], 20, O.REG_PLANE, 1)
+            sc = O.covariances_f64(w["source"], 20, O.REG_PLANE, 1)
+            O.align_gicp_f64(w["target"], tc, w["source"], sc, threads=1)
+            t1.append(time.perf_counter() - t0)
+        config1 = {"value": 1.0 / float(np.median(t1)), "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "3 registrations (median), restated FastGICPSingleThread (k-d tree k=20 covariances + point-to-point GICP, LM), published 9.4 registrations/s on an i9-9900K (README.md:121-122)"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": 1e3 * med * per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": w["data"],
@@ -192,7 +204,8 @@ def run_reference_arm(args, w, rank, world):
                    "registrations_timed": len(times), "statistic": "1 / median registration time", "mean_ms": 1e3 * float(np.mean(times)), "min_ms": 1e3 * float(np.min(times)),
                    "host_cores": os.cpu_count(), "pinned_cpus": "%d-%d (%d threads, one per physical core of NUMA node 0)" % (cpus[0], cpus[-1], threads)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d full registrations (median), restated OpenMP FastVGICP in double (reference not buildable here: no Eigen/PCL), %d pinned threads" % (len(times), threads)},
+                         "sample": "%d full registrations (median), restated OpenMP FastVGICP in double (reference not buildable here: no Eigen/PCL), %d pinned threads" % (len(times), threads),
+                         "config1_fastgicp_single_thread": config1},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -344,59 +344,81 @@ __global__ void __launch_bounds__(128) k_rbf_block_boxes(const float4* __restric
   }
 }
 
-// Stage 1b': covariance_estimation_rbf.cu:59-151.  One query per thread, the points streamed through shared memory in blocks of 512
-// like the reference's per-block async transforms; partial sums per 512-block are folded in block order (the reference's strided
-// finalisation, :92-114).  The reference pads the cloud to a multiple of 512 with points at the origin (:126-129) which pick up
-// weight whenever the query is within max_dist of the origin -- reproduced.  All nine entries of sum w p p^T are kept ((w p_r) p_c
-// and (w p_c) p_r round differently and the reference's Matrix3f holds both).
-// A block whose bounding box is farther than max_dist from the query contributes an all-zero partial (x + 0 == x): it is skipped, and
-// a tile no query of the thread block needs is not even staged.  Scan-ordered LiDAR blocks are compact arcs, so ~90 % are skipped;
-// the float box distance uses the same operations as the per-point distance and rounding is monotone, so it never exceeds it.
+// Stage 1b': covariance_estimation_rbf.cu:59-151.  The reference accumulates, per query, one partial {sum w, sum w p, sum w p p^T}
+// per block of 512 consecutive points (sequentially inside the block, :59-90) and adds the partials in block order (:92-114); the
+// cloud is padded to a multiple of 512 with points at the origin (:126-129) which pick up weight whenever the query is within
+// max_dist of the origin -- all reproduced.  All nine entries of sum w p p^T are kept ((w p_r) p_c and (w p_c) p_r round differently
+// and the reference's Matrix3f holds both).
+// Parallel shape: the blocks of one query are independent, so EIGHT lanes share a query and take the blocks 8 r + lane of round r
+// (16 queries per 128-thread block); after each round the query's first lane adds the eight partials in block order.  That is 8x the
+// threads of a thread-per-query loop (4288 warps instead of 536 at 17 k points: the loop is a latency chain per thread).
+// A block whose bounding box is farther than max_dist from the query contributes an all-zero partial (x + 0 == x) and is skipped; the
+// float box distance uses the same operations as the per-point distance and rounding is monotone, so it never exceeds it.
+constexpr int kRbfLanes = 8;                          // lanes (blocks in flight) per query
+constexpr int kRbfQueries = 128 / kRbfLanes;          // queries per thread block
+constexpr int kRbfTileStride = kRbfBlock + 1;         // float4 per staged tile (+1: the eight tiles start in different banks)
 __global__ void __launch_bounds__(128) k_covariance_rbf(const float4* __restrict__ pts, int n, float exp_factor, float max_dist, int method, const float* __restrict__ boxes,
                                                        float4* __restrict__ covA, float2* __restrict__ covB) {
-  __shared__ float4 tile[kRbfBlock];
-  const int tid = threadIdx.x;
-  const int q = blockIdx.x * blockDim.x + tid;
+  extern __shared__ float4 rbf_tiles[];                                 // [kRbfLanes][kRbfTileStride]
+  __shared__ float part[kRbfQueries][kRbfLanes][13];                    // one partial per (query, lane) and round
+  const int tid = threadIdx.x, ql = tid / kRbfLanes, l = tid % kRbfLanes;
+  const int q = blockIdx.x * kRbfQueries + ql;
   const bool active = q < n;
-  float4 x = active ? pts[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 x = pts[active ? q : n - 1];
   const float max_dist_sq = max_dist * max_dist;
-  float sw = 0.f, m[3] = {0.f, 0.f, 0.f}, c[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // c: row-major
+  float sw = 0.f, m[3] = {0.f, 0.f, 0.f}, c[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // running totals (lane 0 of the query); c row-major
   const int nblocks = (n + kRbfBlock - 1) / kRbfBlock;
-  for (int b = 0; b < nblocks; b++) {
+  for (int r0 = 0; r0 < nblocks; r0 += kRbfLanes) {
+    __syncthreads();  // the previous round's tiles and partials are consumed
+    for (int j = tid; j < kRbfLanes * kRbfBlock; j += 128) {
+      const int t = j / kRbfBlock, jj = j % kRbfBlock;
+      const int g = (r0 + t) * kRbfBlock + jj;
+      rbf_tiles[t * kRbfTileStride + jj] = g < n ? pts[g] : make_float4(0.f, 0.f, 0.f, 0.f);  // padding at the origin, :126-129
+    }
+    __syncthreads();
+    const int b = r0 + l;
+    float psw = 0.f, pm[3] = {0.f, 0.f, 0.f}, pc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bool need = false;
-    if (active) {
+    if (b < nblocks) {
       const float* bx = boxes + b * 6;
       const float dx = fmaxf(fmaxf(bx[0] - x.x, x.x - bx[3]), 0.f), dy = fmaxf(fmaxf(bx[1] - x.y, x.y - bx[4]), 0.f), dz = fmaxf(fmaxf(bx[2] - x.z, x.z - bx[5]), 0.f);
       need = !((dx * dx + dy * dy) + dz * dz > max_dist_sq);
     }
-    if (!__syncthreads_or(need)) continue;  // (also orders the previous tile's reads before the next staging)
-    for (int j = tid; j < kRbfBlock; j += blockDim.x) {
-      int g = b * kRbfBlock + j;
-      tile[j] = g < n ? pts[g] : make_float4(0.f, 0.f, 0.f, 0.f);  // padding at the origin, :126-129
+    if (need) {
+      const float4* tile = rbf_tiles + l * kRbfTileStride;
+      for (int j = 0; j < kRbfBlock; j++) {
+        const float4 p = tile[j];
+        const float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
+        const float sq = (dx * dx + dy * dy) + dz * dz;
+        if (sq > max_dist_sq) continue;
+        const float w = exp_det(-exp_factor * sq);
+        psw += w;
+        const float wx = w * p.x, wy = w * p.y, wz = w * p.z;
+        pm[0] += wx; pm[1] += wy; pm[2] += wz;
+        pc[0] += wx * p.x; pc[1] += wx * p.y; pc[2] += wx * p.z;
+        pc[3] += wy * p.x; pc[4] += wy * p.y; pc[5] += wy * p.z;
+        pc[6] += wz * p.x; pc[7] += wz * p.y; pc[8] += wz * p.z;
+      }
     }
+    float* pp = part[ql][l];
+    pp[0] = psw;
+#pragma unroll
+    for (int d = 0; d < 3; d++) pp[1 + d] = pm[d];
+#pragma unroll
+    for (int d = 0; d < 9; d++) pp[4 + d] = pc[d];
     __syncthreads();
-    if (!need) continue;
-    float psw = 0.f, pm[3] = {0.f, 0.f, 0.f}, pc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < kRbfBlock; j++) {
-      float4 p = tile[j];
-      float dx = x.x - p.x, dy = x.y - p.y, dz = x.z - p.z;
-      float sq = (dx * dx + dy * dy) + dz * dz;
-      if (sq > max_dist_sq) continue;
-      float w = exp_det(-exp_factor * sq);
-      psw += w;
-      float wx = w * p.x, wy = w * p.y, wz = w * p.z;
-      pm[0] += wx; pm[1] += wy; pm[2] += wz;
-      pc[0] += wx * p.x; pc[1] += wx * p.y; pc[2] += wx * p.z;
-      pc[3] += wy * p.x; pc[4] += wy * p.y; pc[5] += wy * p.z;
-      pc[6] += wz * p.x; pc[7] += wz * p.y; pc[8] += wz * p.z;
+    if (l == 0) {  // the reference's finalisation order: partials added block by block
+      for (int t = 0; t < kRbfLanes && r0 + t < nblocks; t++) {
+        const float* s = part[ql][t];
+        sw += s[0];
+#pragma unroll
+        for (int d = 0; d < 3; d++) m[d] += s[1 + d];
+#pragma unroll
+        for (int d = 0; d < 9; d++) c[d] += s[4 + d];
+      }
     }
-    sw += psw;
-#pragma unroll
-    for (int d = 0; d < 3; d++) m[d] += pm[d];
-#pragma unroll
-    for (int d = 0; d < 9; d++) c[d] += pc[d];
   }
-  if (!active) return;
+  if (!active || l != 0) return;
   // NormalDistribution::finalize :47-53:  mean = sum/sw ; cov = (cov - mean*sum^T)/sw
   float mean[3] = {m[0] / sw, m[1] / sw, m[2] / sw};
   float cc[9];
@@ -1155,7 +1177,10 @@ cudaError_t launch_covariance_knn_sharded(const float4* pts, const int* nbr, con
 
 cudaError_t launch_covariance_rbf(const float4* pts, int n, float exp_factor, float max_dist, int method, float* boxes, float4* covA, float2* covB, cudaStream_t stream) {
   k_rbf_block_boxes<<<(n + kRbfBlock - 1) / kRbfBlock, 128, 0, stream>>>(pts, n, boxes);
-  k_covariance_rbf<<<(n + 127) / 128, 128, 0, stream>>>(pts, n, exp_factor, max_dist, method, boxes, covA, covB);
+  const size_t smem = sizeof(float4) * kRbfLanes * kRbfTileStride;
+  cudaError_t e = cudaFuncSetAttribute(k_covariance_rbf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_covariance_rbf<<<(n + kRbfQueries - 1) / kRbfQueries, 128, smem, stream>>>(pts, n, exp_factor, max_dist, method, boxes, covA, covB);
   return cudaGetLastError();
 }
 

@@ -94,6 +94,7 @@ def lib():
         L.orc_evaluate_f32.argtypes = [vp, fp, fp, C.c_int, ip, C.c_int, dp, dp, dp, dp, C.c_int, C.POINTER(C.c_long)]
         L.orc64_covariances.argtypes = [fp, C.c_int, C.c_int, C.c_int, dp, C.c_int]
         L.orc64_align.argtypes = [fp, dp, C.c_int, fp, dp, C.c_int, C.c_double, ip, C.c_int, C.POINTER(LsqParams), dp, C.c_int, C.POINTER(LsqResult)]
+        L.orc64_align_gicp.argtypes = [fp, dp, C.c_int, fp, dp, C.c_int, C.c_double, C.POINTER(LsqParams), dp, C.c_int, C.POINTER(LsqResult)]
         L.orc_num_threads.restype = C.c_int
         L.orc_remove_near_origin.argtypes = [fp, C.c_int, fp]
         L.orc_approximate_voxel_grid.argtypes = [fp, C.c_int, C.c_float, C.c_int, fp]
@@ -372,6 +373,19 @@ def align_f64(target, tgt_cov, source, src_cov, res=1.0, offs=None, guess=None, 
     r = LsqResult()
     lib().orc64_align(_p(target, C.c_float), _p(tgt_cov, C.c_double), len(target), _p(source, C.c_float), _p(src_cov, C.c_double), len(source), float(res), _p(offs, C.c_int),
                       len(offs), C.byref(params), _p(g, C.c_double), threads, C.byref(r))
+    return AlignResult(r)
+
+
+def align_gicp_f64(target, tgt_cov, source, src_cov, max_corr_dist=-1.0, guess=None, params=None, threads=1):
+    """FastGICP / FastGICPSingleThread (fast_gicp_impl.hpp:117-240) restated in double: BASELINE config 1 (CPU timing row)."""
+    target, source = _f32(target), _f32(source)
+    tgt_cov = np.ascontiguousarray(tgt_cov, dtype=np.float64)
+    src_cov = np.ascontiguousarray(src_cov, dtype=np.float64)
+    params = params or default_params()
+    g = _pose_in(np.eye(4) if guess is None else guess)
+    r = LsqResult()
+    lib().orc64_align_gicp(_p(target, C.c_float), _p(tgt_cov, C.c_double), len(target), _p(source, C.c_float), _p(src_cov, C.c_double), len(source), float(max_corr_dist),
+                           C.byref(params), _p(g, C.c_double), int(threads), C.byref(r))
     return AlignResult(r)
 
 

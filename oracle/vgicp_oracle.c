@@ -1387,6 +1387,114 @@ ORC_API int orc64_align(const float* tgt, const double* tgt_cov, int n_tgt, cons
   return 0;
 }
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * FastGICP (BASELINE config 1: the CPU GICP row, single thread or OpenMP)  --  include/fast_gicp/gicp/impl/fast_gicp_impl.hpp
+ *   update_correspondences :117-158 : nearest target point of every transformed source point (float pose and query, k = 1, kd-tree),
+ *                                     accepted below corr_dist_threshold^2; mahalanobis = (C_B + T C_A T^T)^-1 (3x3 block)
+ *   linearize :160-216, compute_error :218-240 : sum e^T M e ; H += J^T M J ; b += J^T M e with J = [skew(T a) | -I], double
+ * ------------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* src; const double* src_cov; int n_src;
+  const float* tgt; const double* tgt_cov; int n_tgt;
+  double corr_dist_sq; int num_threads;
+  KdTree* tree;
+  int* corr;      /* target index or -1 per source point */
+  double* mahal;  /* 9 per source point */
+} GicpProblem;
+
+static void gicp_update_correspondences(GicpProblem* p, const double* T) {
+  float Tf[16];
+  for (int j = 0; j < 16; j++) Tf[j] = (float)T[j];
+  double R[9], Rt[9];
+  for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) { M3(R, r, c) = T[c * 4 + r]; M3(Rt, c, r) = T[c * 4 + r]; }
+#pragma omp parallel for num_threads(p->num_threads) schedule(guided, 8)
+  for (int i = 0; i < p->n_src; i++) {
+    const float* a = p->src + 3 * (size_t)i;
+    float q[3];
+    for (int r = 0; r < 3; r++) q[r] = ((Tf[r] * a[0] + Tf[4 + r] * a[1]) + Tf[8 + r] * a[2]) + Tf[12 + r];
+    float bd[1];
+    int bi[1], cnt = 0;
+    kd_search(p->tree, 0, q, 1, bd, bi, &cnt);
+    p->corr[i] = (cnt > 0 && (double)bd[0] < p->corr_dist_sq) ? bi[0] : -1;
+    if (p->corr[i] < 0) continue;
+    const double* cA = p->src_cov + 9 * (size_t)i;
+    const double* cB = p->tgt_cov + 9 * (size_t)p->corr[i];
+    double t1[9], S[9];
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) M3(t1, r, c) = M3(R, r, 0) * M3(cA, 0, c) + M3(R, r, 1) * M3(cA, 1, c) + M3(R, r, 2) * M3(cA, 2, c);
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) M3(S, r, c) = M3(cB, r, c) + (M3(t1, r, 0) * M3(Rt, 0, c) + M3(t1, r, 1) * M3(Rt, 1, c) + M3(t1, r, 2) * M3(Rt, 2, c));
+    inv3d(S, p->mahal + 9 * (size_t)i);
+  }
+}
+
+static double gicp_eval(GicpProblem* p, const double* T, double* H, double* b) {
+  double sum = 0;
+  const int want = (H && b);
+  const int nt = p->num_threads;
+  double* Hs = (double*)calloc((size_t)nt * 42, sizeof(double));
+#pragma omp parallel for num_threads(nt) reduction(+ : sum) schedule(guided, 8)
+  for (int i = 0; i < p->n_src; i++) {
+    const int it = p->corr[i];
+    if (it < 0) continue;
+    double a[3] = {p->src[3 * (size_t)i], p->src[3 * (size_t)i + 1], p->src[3 * (size_t)i + 2]}, q[3], e[3], Me[3];
+    for (int r = 0; r < 3; r++) q[r] = T[r] * a[0] + T[4 + r] * a[1] + T[8 + r] * a[2] + T[12 + r];
+    const double* M = p->mahal + 9 * (size_t)i;
+    for (int r = 0; r < 3; r++) e[r] = (double)p->tgt[3 * (size_t)it + r] - q[r];
+    for (int r = 0; r < 3; r++) Me[r] = M3(M, r, 0) * e[0] + M3(M, r, 1) * e[1] + M3(M, r, 2) * e[2];
+    sum += e[0] * Me[0] + e[1] * Me[1] + e[2] * Me[2];
+    if (!want) continue;
+    double J[18];
+    memset(J, 0, sizeof(J));
+    J[3 * 1 + 0] = -q[2]; J[3 * 2 + 0] = q[1]; J[3 * 0 + 1] = q[2]; J[3 * 2 + 1] = -q[0]; J[3 * 0 + 2] = -q[1]; J[3 * 1 + 2] = q[0];
+    J[3 * 3 + 0] = -1; J[3 * 4 + 1] = -1; J[3 * 5 + 2] = -1;
+    double JtM[18];
+    for (int r = 0; r < 6; r++) for (int c = 0; c < 3; c++) JtM[r * 3 + c] = J[3 * r] * M3(M, 0, c) + J[3 * r + 1] * M3(M, 1, c) + J[3 * r + 2] * M3(M, 2, c);
+#ifdef _OPENMP
+    double* acc = Hs + (size_t)omp_get_thread_num() * 42;
+#else
+    double* acc = Hs;
+#endif
+    for (int r = 0; r < 6; r++) {
+      for (int c = 0; c < 6; c++) acc[c * 6 + r] += JtM[r * 3] * J[3 * c] + JtM[r * 3 + 1] * J[3 * c + 1] + JtM[r * 3 + 2] * J[3 * c + 2];
+      acc[36 + r] += JtM[r * 3] * e[0] + JtM[r * 3 + 1] * e[1] + JtM[r * 3 + 2] * e[2];
+    }
+  }
+  if (want) {
+    memset(H, 0, 36 * sizeof(double));
+    memset(b, 0, 6 * sizeof(double));
+    for (int t = 0; t < nt; t++) { for (int j = 0; j < 36; j++) H[j] += Hs[(size_t)t * 42 + j]; for (int j = 0; j < 6; j++) b[j] += Hs[(size_t)t * 42 + 36 + j]; }
+  }
+  free(Hs);
+  return sum;
+}
+static double gicp_linearize(void* c, const double* T, double* H, double* b) {
+  gicp_update_correspondences((GicpProblem*)c, T);
+  return gicp_eval((GicpProblem*)c, T, H, b);
+}
+static double gicp_error(void* c, const double* T) { return gicp_eval((GicpProblem*)c, T, NULL, NULL); }
+
+/* FastGICP::align with precomputed double covariances (orc64_covariances); max_corr_dist <= 0: no threshold (the default,
+ * corr_dist_threshold_ = float max, fast_gicp_impl.hpp:29). The kd-tree over the target is part of setInputTarget (:76-84). */
+ORC_API int orc64_align_gicp(const float* tgt, const double* tgt_cov, int n_tgt, const float* src, const double* src_cov, int n_src, double max_corr_dist,
+                             const OrcLsqParams* params, const double* guess, int num_threads, OrcLsqResult* res_out) {
+  GicpProblem p;
+  memset(&p, 0, sizeof(p));
+#ifdef _OPENMP
+  if (num_threads <= 0) num_threads = omp_get_max_threads();
+#else
+  num_threads = 1;
+#endif
+  p.src = src; p.src_cov = src_cov; p.n_src = n_src; p.tgt = tgt; p.tgt_cov = tgt_cov; p.n_tgt = n_tgt;
+  p.corr_dist_sq = max_corr_dist > 0 ? max_corr_dist * max_corr_dist : 1e300;
+  p.num_threads = num_threads;
+  p.tree = kd_build(tgt, n_tgt);
+  p.corr = (int*)malloc(sizeof(int) * (size_t)(n_src > 0 ? n_src : 1));
+  p.mahal = (double*)malloc(sizeof(double) * 9 * (size_t)(n_src > 0 ? n_src : 1));
+  lsq_optimize(params, &p, gicp_linearize, gicp_error, guess, res_out);
+  kd_free(p.tree);
+  free(p.corr); free(p.mahal);
+  return 0;
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -209,3 +209,14 @@ def test_rbf_covariances_against_direct_evaluation(pair02, relative_pose):
     r = O.register_f32(tgt, src, method=O.DIRECT1, knn_method="rbf")
     dt, dr = pose_error(relative_pose, r.T)
     assert r.converged and dt < T_TOL and dr < R_TOL, (dt, dr)
+
+
+def test_fastgicp_restatement_meets_the_reference_gate(pair02, relative_pose):
+    """FastGICP (fast_gicp_impl.hpp:117-240; BASELINE config 1, the single-thread CPU row): the restatement converges to
+    data/relative.txt within the reference test's tolerance (src/test/gicp_test.cpp:147-201 runs the same gate on GICP)."""
+    tgt, src = pair02
+    tc = O.covariances_f64(tgt, 20, O.REG_PLANE, 1)
+    sc = O.covariances_f64(src, 20, O.REG_PLANE, 1)
+    r = O.align_gicp_f64(tgt, tc, src, sc, threads=1)
+    dt, dr = pose_error(relative_pose, r.T)
+    assert r.converged and dt < T_TOL and dr < R_TOL, (dt, dr)
