@@ -9,8 +9,9 @@ voxel_res 1.0, k=20, PLANE, LM defaults, identity initial guess.
 
 One registration follows the reference's "100times" protocol (src/align.cpp:72-81): clearTarget, clearSource,
 setInputTarget (upload, kNN, covariances, voxel map), setInputSource (upload, kNN, covariances), align.
-One *step* = one registration on each of S concurrent streams of the GPU (--streams, default 16: one host thread and one
-handle per stream; a 17k-pt registration is a chain of small latency-bound kernels, so one stream cannot fill 148 SMs).
+One *step* = one registration on each of S concurrent streams of the GPU (--streams, default 8 at every N: one host thread and one
+handle per stream; a 17k-pt registration is a chain of small latency-bound kernels, so one stream cannot fill 148 SMs; the rate
+saturates at 8 streams).  Host threads are pinned to the cores of the GPU's NUMA node, an own slice per rank.
 
   value  : registrations/s with the clouds already resident in HBM when the timed region starts (device pointers
            through the C ABI); device time from a common start event to the last stream's end event; every registration
@@ -18,12 +19,18 @@ handle per stream; a 17k-pt registration is a chain of small latency-bound kerne
   e2e    : the same through the reference-facing class FastVGICPCuda with HOST (pinned) buffers: H2D of both clouds and D2H
            of the aligned cloud + pose inside the timed region.
   single_stream: the sequential protocol on one stream (latency), L2 flushed between registrations.
-  roofline: dominant kernel of the step, algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json.
+  roofline: dominant kernel group of the step, algorithmic bytes (SURVEY.md 8d) / CUDA-event time, against MEASURED_PEAKS.json;
+           traffic = ncu DRAM bytes (profiles/traffic.json, quoted only while it matches the CUDA sources being run).
   cpu_baseline: the reference's own CPU implementation of the path (OpenMP FastVGICP, restated in oracle/ because the
-           reference cannot be compiled here) on the box's host cores, bounded sample.
+           reference cannot be compiled here) on 32 pinned host cores, median of >= 30 registrations; plus the FastGICP single-thread
+           row of BASELINE config 1.
+  published_configurations: the same pair as the reference's README rows run it (DIRECT1; DIRECT1 with RBF covariances).
+  c4     : BASELINE config 4, the 1M-point pair: stage times and the evaluation kernel's HBM roofline (DIRECT27 and DIRECT1) on one
+           GPU; with N > 1 the same registration with stage 1 and stage 3 sharded over the N ranks (in-kernel NVLink exchanges),
+           speed-up against the unsharded registration measured in the same run, agreement and bit-identity across ranks.
 
-N>1 (torchrun): the 17k-pt path does not shard usefully -> replicas, one registration stream per GPU, no
-data-path collective; value = N*K registrations / max-over-ranks time ("weak" scaling).
+N>1 (torchrun): the 17k-pt path does not shard usefully -> replicas, S registration streams per GPU, no
+data-path collective; value = N*S*K registrations / max-over-ranks time ("weak" scaling).  The c4 record is the sharded path.
 """
 import argparse
 import json

@@ -42,6 +42,6 @@ print("ndt d2d", "converged", bool(r.converged))
 c.close()
 PY
 for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_driver.py > gpurun_out/sanitizer_$tool.log 2>&1
-  echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer_$tool.log | tail -1)"
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_driver.py > gpurun_out/r02_sanitizer_$tool.log 2>&1
+  echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/r02_sanitizer_$tool.log | tail -1)"
 done
