@@ -18,9 +18,10 @@ WORKER = textwrap.dedent(
     mx = D.max_over_ranks(ms)
     value, worst = D.aggregate_throughput(local_units=100 * (rank + 1), local_ms=20.0 * (rank + 1))
     lo, hi = D.partition(11, rank, world)
+    handles = D._all_gather_bytes(bytes([rank] * 64))  # the transport of the 64-byte IPC handles of the sharded path
     D.barrier()
     if rank == 0:
-        print(json.dumps({"mx": mx, "value": value, "worst": worst, "part": [lo, hi], "world": world}))
+        print(json.dumps({"mx": mx, "value": value, "worst": worst, "part": [lo, hi], "world": world, "handles": [list(h[:2]) + [len(h)] for h in handles]}))
     else:
         print(json.dumps({"part": [lo, hi]}))
     D.finalize()
@@ -54,3 +55,4 @@ def test_replica_plumbing_world2(tmp_path):
     assert abs(r0["value"] - 300 / 0.040) < 1e-6   # (100 + 200) units / slowest rank (40 ms)
     assert r0["worst"] == 40.0
     assert r0["part"] == [0, 6] and r1["part"] == [6, 11]
+    assert r0["handles"] == [[0, 0, 64], [1, 1, 64]]  # rank order, 64 bytes each

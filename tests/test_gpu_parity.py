@@ -656,6 +656,53 @@ def test_caller_supplied_covariances(prepared, relative_pose):
     c.close()
 
 
+def test_abi_guards_added_in_round_2(prepared):
+    """set_*_neighbors rejects an index outside the cloud (it would be an illegal address in the covariance kernel and poison the
+    context of every handle of the process); vgicp_register carries on after NORMALIZED_MIN_EIG like the class wrappers do (the
+    reference prints "unimplemented ..." and keeps the raw covariances, covariance_regularization.cu:121-123)."""
+    from fast_gicp_b200.core import ERR_INVALID_ARGUMENT, Core, VgicpError
+
+    c = Core(0)
+    c.set_source_cloud(prepared["src"])
+    bad = prepared["s_nbr"].copy()
+    bad[123, 7] = len(prepared["src"])
+    with pytest.raises(VgicpError) as e:
+        c.set_source_neighbors(20, bad)
+    assert e.value.code == ERR_INVALID_ARGUMENT
+    bad[123, 7] = -1
+    with pytest.raises(VgicpError):
+        c.set_source_neighbors(20, bad)
+    c.set_source_neighbors(20, prepared["s_nbr"])  # the handle is still usable
+    c.calculate_source_covariances(O.REG_NONE)
+    assert np.array_equal(c.get_source_covariances(), prepared["s_raw"])
+    r = c.register(prepared["tgt"], prepared["src"], reg=O.REG_NORMALIZED_MIN_EIG)
+    assert r.nr_iterations >= 0  # ran to the end with the raw covariances instead of failing on VGICP_ERR_UNSUPPORTED
+    c.close()
+
+
+def test_ndt_maps_are_kept_like_the_reference(pair02):
+    """NDTCudaCore::create_{source,target}_voxelmap return early when the map exists (ndt_cuda.cu:123-141): a second create (or a
+    second align) neither rebuilds the maps nor picks up a new resolution; set_*_cloud resets that cloud's map only."""
+    from fast_gicp_b200.core import Core
+
+    tgt, src = pair02
+    c = Core(0)
+    c.set_problem(2)
+    c.set_resolution(1.0)
+    c.set_target_cloud(tgt)
+    c.set_source_cloud(src)
+    c.ndt_create_voxelmaps()
+    v1, n0 = c.num_voxels(), c.launch_count()
+    c.set_resolution(0.5)
+    c.ndt_create_voxelmaps()  # both maps exist: nothing happens
+    assert c.num_voxels() == v1 and c.launch_count() == n0
+    c.set_target_cloud(tgt)   # resets the target map: rebuilt with the resolution current now
+    c.ndt_create_voxelmaps()
+    assert c.num_voxels() > v1
+    assert c.num_voxels() == O.VoxelMap(tgt, None, 0.5, accum_double=True).num_voxels
+    c.close()
+
+
 def _rbf_cloud():
     rng = np.random.default_rng(2)
     pts = (rng.normal(size=(1500, 3)) * [3.0, 3.0, 0.2]).astype(np.float32)
