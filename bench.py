@@ -741,7 +741,7 @@ def main():
         "compute_error": 52.0 * n_s + 52.0 * V + 16.0 * B,
     }
     # kernel groups as they appear in the ncu launch list: the evaluation kernel k_linearize<MODE,WANT_H,G> (linearize and
-    # error-only calls are the same template), the k-NN stage (grid build + k_knn_grid + k_knn_grid_heavy), ...
+    # error-only calls are the same template), the k-NN stage (Morton grid build + k_knn_search + k_knn_deferred), ...
     groups = {"evaluate (k_linearize, H and error-only)": ["linearize", "compute_error"], "knn stage (k_grid_* + k_sort_pass + k_knn_search + k_knn_deferred)": ["knn"],
               "covariance (k_covariance_knn)": ["covariance"], "voxelmap_build (table, ids, sort, ordered per-voxel sums)": ["voxelmap_build"]}
     total_kernel_ms = sum(v["ms_per_step"] for v in per_kernel.values()) or 1.0

@@ -1,4 +1,4 @@
-"""Time the kNN stage alone (grid build + k_knn_grid + k_knn_grid_heavy) on the fixture target cloud: wall clock over a loop of
+"""Time the kNN stage alone (Morton grid build + k_knn_search + k_knn_deferred) on the fixture target cloud: wall clock over a loop of
 find_target_neighbors + synchronize on one stream, and the per-category device times from the profiling hooks."""
 import sys, time, numpy as np
 sys.path.insert(0, ".")

@@ -18,7 +18,7 @@ for method, knn_mode, align_mode, hint, vindex, spec in (("DIRECT27", 0, 1, 0, 0
     c.calculate_source_covariances_rbf(3)
     print(method, "converged", bool(r.converged), "fitness", c.fitness_score(np.eye(4)))
     c.close()
-# a far outlier: the voxel bounding box no longer fits the direct-mapped index, the k-NN ladder degenerates to the block-cooperative scan
+# a far outlier: the voxel bounding box no longer fits the direct-mapped index, the k-NN grid's levels are all coarse there and the deferred (block-cooperative) search takes the queries
 c = Core(0)
 c.set_neighbor_search_method("DIRECT27")
 far = np.vstack([tgt, np.array([[3.0e6, -2.0e6, 1.0e6]], dtype=np.float32)])
