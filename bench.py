@@ -44,6 +44,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# 8 handles x 2 streams alias onto the default 8 hardware work queues and wait on each other; 32 queues (read by the driver when the context is
+# created) give +5..9 % registrations/s at 8 handles, +20 % at 16 (profiles/r02_connections_sweep.txt).  fast_gicp_b200.core sets the same default.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 _REAL_STDOUT = sys.stdout
 METRIC = "registrations/sec (VGICP, ~17k-pt pairs)"
@@ -792,7 +795,7 @@ def main():
         "metric": METRIC_NAME, "value": world * S * K / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": w["data"],
         "config": {"workload": w["name"], "protocol": "align.cpp 100times (covariances recomputed every registration)", "step": "one registration on each of the %d concurrent streams of a GPU (one host thread + one handle per stream)" % S,
-                   "streams_per_gpu": S, "registrations_per_step": S * world, "execution_hint": "throughput" if hint else "latency",
+                   "streams_per_gpu": S, "cuda_device_max_connections": int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8")), "registrations_per_step": S * world, "execution_hint": "throughput" if hint else "latency",
                    "l2": "inputs larger than L2: each registration takes the next of %d distinct pairs (%.0f MB pool)" % (P, P * pair_bytes / 1e6),
                    "parallelism": "replicas x%d" % world, "n_target": n_t, "n_source": n_s, "num_voxels": V, "num_buckets": B,
                    "lm_iterations": int(res.nr_iterations) + 1, "evaluations": int(res.n_linearize + res.n_compute_error), "converged": bool(res.converged)},

@@ -9,6 +9,10 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# Several handles in one process (each owns two streams) alias onto the default 8 hardware work queues and wait on each other; the driver reads
+# this when the context is created.  Measured: +5..9 % registrations/s at 8 handles, +20 % at 16 (profiles/r02_connections_sweep.txt).  A value
+# the caller has set wins.  C/C++ callers export it themselves.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 LIB_PATH = os.environ.get("VGICP_B200_LIB") or os.path.join(_HERE, "lib", "libvgicp_b200.so")  # override only for A/B experiments
 
 OK, ERR_INVALID_ARGUMENT, ERR_BAD_STATE, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_COMM = range(7)

@@ -7,7 +7,8 @@
  * on one handle exactly as a sequential caller would run it, so the results are those of the sequential loop, bit for bit,
  * whatever the interleaving.  (SURVEY.md 8b lists it as the `vgicp_batch_align` extension.)
  *
- * STATUS (round 1): compiled and ABI-checked on the CPU; the GPU test (tests/test_batch.py) has not run on hardware yet. */
+ * Checked on a B200 by tests/test_batch.py (24 pairs over 6 handles against the sequential loop: same poses, counters and aligned clouds,
+ * bit for bit).  A device-batched execution path (one launch per stage over all pairs) is not built: DESIGN.md 8. */
 #ifndef VGICP_BATCH_B200_H
 #define VGICP_BATCH_B200_H
 #include <stddef.h>
